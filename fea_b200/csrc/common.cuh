@@ -1,0 +1,97 @@
+// Shared device/host helpers for libfea_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fea_b200.h"
+
+namespace fea {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Last CUDA error seen by any entry point (reported by fea_last_cuda_error()).
+void set_last_error(cudaError_t e);
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error(e);
+    return FEA_ERR_CUDA;
+  }
+  return FEA_OK;
+}
+
+inline int check(cudaError_t e) {
+  if (e != cudaSuccess) {
+    set_last_error(e);
+    return FEA_ERR_CUDA;
+  }
+  return FEA_OK;
+}
+
+#define FEA_TRY(expr)                    \
+  do {                                   \
+    int _rc = (expr);                    \
+    if (_rc != FEA_OK) return _rc;       \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32).  Result valid in thread 0.
+// `scratch` is >= 32 doubles of shared memory.  Fixed reduction tree => deterministic.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect scratch reuse
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    t = lane < nw ? scratch[lane] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;
+}
+
+// Record a data-dependent error in a zero-initialised slot: status[0] = max code seen,
+// status[1] = 0x7fffffff - (smallest offending index)  (atomicMax keeps the smallest index).
+__device__ __forceinline__ void raise_status(int32_t* status, int code, int index) {
+  if (status == nullptr) return;
+  atomicMax(&status[0], code);
+  atomicMax(&status[1], 0x7fffffff - index);
+}
+
+// Streaming (evict-first) loads for data read exactly once per kernel: keeps L2 for the vectors.
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+
+// Device-wide exclusive scan of int32 (out has n+1 entries, out[n] = total).
+// `block_sums` needs ceil(n / kScanChunk) + 1 ints.  Also writes max(in) to *max_out if non-null.
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* block_sums,
+                       int32_t* max_out, cudaStream_t stream);
+inline size_t scan_workspace_ints(int64_t n) { return (size_t)ceil_div(n, kScanChunk) + 2; }
+
+}  // namespace fea

@@ -1,0 +1,184 @@
+// Library identification, multi-RHS SpMM and the adjacent steps of the reference scripts
+// (SURVEY.md §8(f)): member forces (truss.py:78-92), beam moment/shear (euler_bernoulli.py:76-102),
+// mesh extrusion (utils.py:356-376).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace fea {
+
+static char g_err[256] = "";
+
+void set_last_error(cudaError_t e) {
+  std::snprintf(g_err, sizeof(g_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+// Y = K X, X/Y (n_dof, R) row-major.  Warp per node; lane <-> CPL adjacent right-hand sides of a
+// 32*CPL-wide column tile.  Matrix values are warp-uniform (broadcast) loads; X rows are read as
+// coalesced 256*CPL-byte segments.
+template <int D, int CPL>
+__global__ void __launch_bounds__(256)
+spmm_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
+            const double* __restrict__ values, const double* __restrict__ X, double* __restrict__ Y, int R) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int tiles = (R + 32 * CPL - 1) / (32 * CPL);
+  for (int64_t node = warp_global; node < n_nodes; node += n_warps) {
+    const int lo = node_rowptr[node];
+    const int cnt = node_rowptr[node + 1] - lo;
+    const int row_len = D * cnt;
+    const double* v = values + (int64_t)(D * D) * lo;
+    for (int tile = 0; tile < tiles; ++tile) {
+      const int col0 = tile * 32 * CPL + lane * CPL;
+      double acc[D][CPL];
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) acc[a][j] = 0.0;
+      for (int k = 0; k < cnt; ++k) {
+        const int64_t xrow = (int64_t)D * node_colidx[lo + k];
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
+          double xv[CPL];
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) xv[j] = col0 + j < R ? X[(xrow + b) * R + col0 + j] : 0.0;
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            const double m = v[a * row_len + D * k + b];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) acc[a][j] = fma(m, xv[j], acc[a][j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+          if (col0 + j < R) Y[(node * D + a) * R + col0 + j] = acc[a][j];
+    }
+  }
+}
+
+__global__ void truss_member_forces_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ members,
+                                           const double* __restrict__ k, int64_t n_members,
+                                           const double* __restrict__ displaced, double* __restrict__ forces) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_members) return;
+  const int64_t a = members[2 * m], b = members[2 * m + 1];
+  double d0[3], d1[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    d0[c] = nodes[3 * b + c] - nodes[3 * a + c];
+    d1[c] = displaced[3 * b + c] - displaced[3 * a + c];
+  }
+  const double l0 = sqrt(d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2]);
+  const double l1 = sqrt(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
+  const double force = -k[m] * (l0 - l1);  // truss.py:84-88
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double fv = force * d1[c] / l1;  // truss.py:89-90
+    atomicAdd(&forces[3 * a + c], fv);     // truss.py:91
+    atomicAdd(&forces[3 * b + c], -fv);    // truss.py:92
+  }
+}
+
+__global__ void beam_moment_shear_kernel(const double* __restrict__ u, const double* __restrict__ EI,
+                                         const double* __restrict__ length, int64_t n_elem,
+                                         double* __restrict__ moment, double* __restrict__ shear) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_elem) return;
+  if (i == n_elem) {  // the reference leaves the last node's entries at 0 (quirk Q7)
+    moment[i] = 0.0;
+    shear[i] = 0.0;
+    return;
+  }
+  const double L = length[i], ei = EI[i];
+  const double u0 = u[2 * i], u1 = u[2 * i + 1], u2 = u[2 * i + 2], u3 = u[2 * i + 3];
+  moment[i] = ei / (L * L) * (12 * u0 - 6 * L * u1 - 12 * u2 + 6 * L * u3);                          // :81-91
+  shear[i] = ei / (L * L * L) * (6 * L * u0 + 2 * (L * L) * u1 - 6 * L * u2 + 4 * (L * L) * u3);    // :92-102
+}
+
+__global__ void mesh_extrude_kernel(const double* __restrict__ nodes2d, int64_t n2d, const int32_t* __restrict__ faces2d,
+                                    int64_t n_faces, const double* __restrict__ z, int64_t n_layers,
+                                    double* __restrict__ nodes3d, int32_t* __restrict__ elements) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = tid; i < n2d * n_layers; i += stride) {  // utils.py:363-365
+    const int64_t layer = i / n2d, j = i - layer * n2d;
+    nodes3d[3 * i] = nodes2d[2 * j];
+    nodes3d[3 * i + 1] = nodes2d[2 * j + 1];
+    nodes3d[3 * i + 2] = z[layer];
+  }
+  for (int64_t e = tid; e < n_faces * (n_layers - 1); e += stride) {  // utils.py:368-374
+    const int64_t layer = e / n_faces, f = e - layer * n_faces;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int32_t v = faces2d[4 * f + c];
+      elements[8 * e + c] = (int32_t)(v + layer * n2d);
+      elements[8 * e + 4 + c] = (int32_t)(v + (layer + 1) * n2d);
+    }
+  }
+}
+
+}  // namespace fea
+
+using namespace fea;
+
+extern "C" const char* fea_version(void) { return "fea_b200 0.1.0 sm_100a"; }
+extern "C" const char* fea_last_cuda_error(void) { return g_err; }
+
+template <int D>
+static int launch_spmm(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values, const double* X,
+                       double* Y, int R, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_nodes, 8), 148LL * 16));
+  if (R > 32)
+    spmm_kernel<D, 2><<<blocks, 256, 0, stream>>>(n_nodes, rp, ci, values, X, Y, R);
+  else
+    spmm_kernel<D, 1><<<blocks, 256, 0, stream>>>(n_nodes, rp, ci, values, X, Y, R);
+  return check_launch();
+}
+
+extern "C" int fea_spmm(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, const int32_t* node_colidx,
+                        const double* values, const double* X, double* Y, int32_t n_rhs, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!node_rowptr || !node_colidx || !values || !X || !Y || n_nodes <= 0 || n_rhs < 1) return FEA_ERR_INVALID;
+  switch (d) {
+    case 1: return launch_spmm<1>(n_nodes, node_rowptr, node_colidx, values, X, Y, n_rhs, stream);
+    case 2: return launch_spmm<2>(n_nodes, node_rowptr, node_colidx, values, X, Y, n_rhs, stream);
+    case 3: return launch_spmm<3>(n_nodes, node_rowptr, node_colidx, values, X, Y, n_rhs, stream);
+    default: return FEA_ERR_INVALID;
+  }
+}
+
+extern "C" int fea_truss_member_forces(const double* nodes, const int32_t* members, const double* k,
+                                       int64_t n_members, const double* displaced, double* forces, void* stream_) {
+  if (!nodes || !members || !k || !displaced || !forces || n_members < 0) return FEA_ERR_INVALID;
+  if (n_members == 0) return FEA_OK;
+  truss_member_forces_kernel<<<(unsigned)ceil_div(n_members, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      nodes, members, k, n_members, displaced, forces);
+  return check_launch();
+}
+
+extern "C" int fea_beam_moment_shear(const double* u, const double* EI, const double* length, int64_t n_elem,
+                                     double* moment, double* shear, void* stream_) {
+  if (!u || !EI || !length || !moment || !shear || n_elem < 0) return FEA_ERR_INVALID;
+  beam_moment_shear_kernel<<<(unsigned)ceil_div(n_elem + 1, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      u, EI, length, n_elem, moment, shear);
+  return check_launch();
+}
+
+extern "C" int fea_mesh_extrude(const double* nodes2d, int64_t n2d, const int32_t* faces2d, int64_t n_faces,
+                                const double* z_heights, int64_t n_layers, double* nodes3d, int32_t* elements,
+                                void* stream_) {
+  if (!nodes2d || !faces2d || !z_heights || !nodes3d || !elements || n2d <= 0 || n_faces < 0 || n_layers < 1)
+    return FEA_ERR_INVALID;
+  if (n2d * n_layers >= (int64_t)INT32_MAX) return FEA_ERR_INVALID;
+  const int64_t work = std::max(n2d * n_layers, n_faces * (n_layers - 1));
+  const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, 256), 148LL * 32));
+  mesh_extrude_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(nodes2d, n2d, faces2d, n_faces,
+                                                                            z_heights, n_layers, nodes3d, elements);
+  return check_launch();
+}

@@ -1,0 +1,431 @@
+// SpMV entry points and the Jacobi-preconditioned conjugate-gradient solver.
+//
+// Replaces `np.linalg.solve(reduced_K, reduced_forces)` (cubebeam.py:98, fea.py:105,
+// euler_bernoulli.py:69 -- the author's "# TODO iterative solver", cubebeam.py:99) and the
+// reaction product `K @ u` (cubebeam.py:106).
+//
+// Dirichlet elimination costs nothing at solve time: constrained DOF carry dinv = 0, hence
+// z = dinv r, p and x stay exactly 0 there, their columns contribute nothing to K p, and their
+// rows never enter a dot product (every dot is weighted by dinv or masked by dinv != 0).  The
+// iteration is therefore the PCG of the reference's reduced system K_ff u_f = f_f.
+//
+// One iteration = 3 kernels, all HBM-bound, no host synchronisation:
+//   step 1  ap = K p                       + partial sums of p.ap          (fused in the SpMV)
+//   step 2  x += a p;  r -= a ap           + partial sums of r.dinv.r, r.r (fused)
+//   step 3  p = dinv r + (rz_new/rz) p     + convergence test / bookkeeping in the last block
+// Cross-block reductions: per-block partial -> last block to finish sums them in a fixed order
+// (deterministic; no floating-point atomics).  Every kernel starts with `if (done) return`, so
+// the host enqueues iterations in chunks and polls a pinned copy of the state without ever
+// stalling the GPU.
+#include <algorithm>
+#include <cmath>
+
+#include "spmv.cuh"
+
+namespace fea {
+
+// Device-resident solver state (FEA_PCG_STATE_BYTES = 256 bytes).
+struct PcgState {
+  double rz;       // FEA_PCG_RZ      r.z of the current iterate
+  double bnorm2;   // FEA_PCG_BNORM2  ||b||^2 over free DOF
+  double rz_new;   // FEA_PCG_RZ_NEW
+  double rr;       // FEA_PCG_RR      ||r||^2 over free DOF
+  double pap;      // FEA_PCG_PAP
+  double tol2;     // FEA_PCG_TOL2
+  double spare[10];
+  int32_t iter;      // int32 index 32
+  int32_t done;      // 33
+  int32_t status;    // 34
+  int32_t max_iter;  // 35
+  uint32_t counter[4];
+  int32_t pad[24];
+};
+static_assert(sizeof(PcgState) == FEA_PCG_STATE_BYTES, "PcgState layout");
+
+// Block partial -> global slot; returns true in the last block to finish (all threads).
+__device__ __forceinline__ bool publish_partials(double* partials, int n_scalars, const double* vals,
+                                                 uint32_t* counter) {
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_scalars; ++s) partials[s * kMaxPartials + blockIdx.x] = vals[s];
+    __threadfence();
+    const uint32_t ticket = atomicAdd(counter, 1u);
+    s_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  return s_last;
+}
+
+// Sum of partials[0..gridDim.x) in a fixed order; result valid in thread 0.
+__device__ __forceinline__ double reduce_partials(const double* partials, double* scratch) {
+  double t = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(partials + i);
+  return block_sum(t, scratch);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kSpmvThreads) spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr,
+                                                            const int32_t* __restrict__ node_colidx,
+                                                            const double* __restrict__ values,
+                                                            const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t node = (int64_t)blockIdx.x * kSpmvWarps + warp; node < n_nodes;
+       node += (int64_t)gridDim.x * kSpmvWarps) {
+    const int lo = node_rowptr[node];
+    const int cnt = node_rowptr[node + 1] - lo;
+    double out[D];
+    spmv_node<D>(node_colidx, values, x, lo, cnt, lane, out);
+    if (lane < D) {
+      double o = out[0];
+#pragma unroll
+      for (int a = 1; a < D; ++a) o = lane == a ? out[a] : o;
+      y[node * D + lane] = o;
+    }
+  }
+}
+
+// step 1: ap = K p over the owned nodes, fused with the partial p.ap.
+template <int D>
+__global__ void __launch_bounds__(kSpmvThreads)
+pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
+                const double* __restrict__ values, const double* __restrict__ p, double* __restrict__ ap,
+                int64_t p_row_offset, PcgState* st, double* partials) {
+  __shared__ double s_red[32];
+  if (st->done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* p_own = p + p_row_offset * D;
+  double dot = 0.0;
+  for (int64_t node = (int64_t)blockIdx.x * kSpmvWarps + warp; node < n_nodes;
+       node += (int64_t)gridDim.x * kSpmvWarps) {
+    const int lo = node_rowptr[node];
+    const int cnt = node_rowptr[node + 1] - lo;
+    double out[D];
+    spmv_node<D>(node_colidx, values, p, lo, cnt, lane, out);
+    if (lane < D) {
+      double o = out[0];
+#pragma unroll
+      for (int a = 1; a < D; ++a) o = lane == a ? out[a] : o;
+      ap[node * D + lane] = o;
+      dot = fma(o, p_own[node * D + lane], dot);
+    }
+  }
+  const double total = block_sum(dot, s_red);
+  if (publish_partials(partials, 1, &total, &st->counter[0])) {
+    const double s = reduce_partials(partials, s_red);
+    if (threadIdx.x == 0) {
+      st->pap = s;
+      st->counter[0] = 0;
+    }
+  }
+}
+
+// step 2
+__global__ void __launch_bounds__(256)
+pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ p,
+                  const double* __restrict__ ap, double* __restrict__ x, double* __restrict__ r, PcgState* st,
+                  double* partials) {
+  __shared__ double s_red[32];
+  if (st->done) return;
+  const double pap = st->pap, rz = st->rz;
+  if (st->bnorm2 == 0.0 || !(pap > 0.0)) {  // zero right-hand side, or K_ff not positive definite
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st->done = 1;
+      st->status = st->bnorm2 == 0.0 ? FEA_OK : FEA_ERR_BREAKDOWN;
+    }
+    return;
+  }
+  const double alpha = rz / pap;
+  double s_rz = 0.0, s_rr = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double di = dinv[i];
+    const double pi = p[i];
+    const double ri = fma(-alpha, ap[i], r[i]);
+    x[i] = fma(alpha, pi, x[i]);
+    r[i] = ri;
+    if (di != 0.0) {
+      s_rz = fma(ri * di, ri, s_rz);
+      s_rr = fma(ri, ri, s_rr);
+    }
+  }
+  double tot[2];
+  tot[0] = block_sum(s_rz, s_red);
+  tot[1] = block_sum(s_rr, s_red);
+  if (publish_partials(partials, 2, tot, &st->counter[1])) {
+    const double a = reduce_partials(partials, s_red);
+    const double b = reduce_partials(partials + kMaxPartials, s_red);
+    if (threadIdx.x == 0) {
+      st->rz_new = a;
+      st->rr = b;
+      st->iter += 1;
+      st->counter[1] = 0;
+    }
+  }
+}
+
+// step 3
+__global__ void __launch_bounds__(256)
+pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
+                     double* __restrict__ p, PcgState* st, double* history) {
+  __shared__ bool s_last;
+  if (st->done) return;
+  const double rz = st->rz, rz_new = st->rz_new;
+  const bool converged = st->rr <= st->tol2 * st->bnorm2;
+  if (!converged) {
+    const double beta = rz_new / rz;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      p[i] = fma(beta, p[i], dinv[i] * r[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&st->counter[2], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    if (history != nullptr && st->iter >= 1 && st->iter <= st->max_iter)
+      history[st->iter - 1] = sqrt(st->rr / st->bnorm2);
+    if (converged) {
+      st->done = 1;
+    } else {
+      st->rz = rz_new;
+      if (st->iter >= st->max_iter) {
+        st->done = 1;
+        st->status = FEA_ERR_MAXITER;
+      }
+    }
+    st->counter[2] = 0;
+  }
+}
+
+// x = 0, r = b on free DOF (0 on constrained), p = dinv r; partial r.z and ||b||^2.
+__global__ void __launch_bounds__(256)
+pcg_init_kernel(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
+                double* __restrict__ r, double* __restrict__ p, double tol, int max_iter, PcgState* st,
+                double* partials) {
+  __shared__ double s_red[32];
+  double s_rz = 0.0, s_bb = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double di = dinv[i];
+    const double ri = di != 0.0 ? b[i] : 0.0;
+    const double zi = di * ri;
+    x[i] = 0.0;
+    r[i] = ri;
+    p[i] = zi;
+    s_rz = fma(ri, zi, s_rz);
+    s_bb = fma(ri, ri, s_bb);
+  }
+  double tot[2];
+  tot[0] = block_sum(s_rz, s_red);
+  tot[1] = block_sum(s_bb, s_red);
+  if (publish_partials(partials, 2, tot, &st->counter[3])) {
+    const double a = reduce_partials(partials, s_red);
+    const double c = reduce_partials(partials + kMaxPartials, s_red);
+    if (threadIdx.x == 0) {
+      st->rz = a;
+      st->bnorm2 = c;
+      st->rz_new = 0.0;
+      st->rr = c;
+      st->pap = 0.0;
+      st->tol2 = tol * tol;
+      st->iter = 0;
+      st->done = 0;
+      st->status = FEA_OK;
+      st->max_iter = max_iter;
+      st->counter[0] = st->counter[1] = st->counter[2] = st->counter[3] = 0;
+    }
+  }
+}
+
+inline unsigned vec_blocks(int64_t n) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 4), 148LL * 8));
+}
+inline unsigned spmv_blocks(int64_t n_nodes) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_nodes, kSpmvWarps), 148LL * 8));
+}
+
+struct PcgWork {
+  PcgState* state;
+  double* partials;  // 2 * kMaxPartials
+  double* r;
+  double* p;
+  double* ap;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static PcgWork carve_pcg(void* work, int64_t n) {
+  PcgWork w;
+  char* c = static_cast<char*>(work);
+  w.state = reinterpret_cast<PcgState*>(c);
+  c += FEA_PCG_STATE_BYTES;
+  w.partials = reinterpret_cast<double*>(c);
+  c += sizeof(double) * 2 * kMaxPartials;
+  const size_t vec = align_up(sizeof(double) * (size_t)n, 256);
+  w.r = reinterpret_cast<double*>(c);
+  c += vec;
+  w.p = reinterpret_cast<double*>(c);
+  c += vec;
+  w.ap = reinterpret_cast<double*>(c);
+  return w;
+}
+
+template <int D>
+static int launch_step_spmv(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
+                            const double* p, double* ap, int64_t off, PcgState* st, double* partials,
+                            cudaStream_t stream) {
+  pcg_spmv_kernel<D><<<spmv_blocks(n_nodes), kSpmvThreads, 0, stream>>>(n_nodes, rp, ci, values, p, ap, off, st,
+                                                                        partials);
+  return FEA_OK;
+}
+
+static int step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
+                     const double* p, double* ap, int64_t off, PcgState* st, double* partials, cudaStream_t stream) {
+  switch (d) {
+    case 1: return launch_step_spmv<1>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
+    case 2: return launch_step_spmv<2>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
+    case 3: return launch_step_spmv<3>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
+    default: return FEA_ERR_INVALID;
+  }
+}
+
+}  // namespace fea
+
+using namespace fea;
+
+extern "C" int fea_spmv(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, const int32_t* node_colidx,
+                        const double* values, const double* x, double* y, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!node_rowptr || !node_colidx || !values || !x || !y || n_nodes <= 0) return FEA_ERR_INVALID;
+  const unsigned blocks = spmv_blocks(n_nodes);
+  switch (d) {
+    case 1: spmv_kernel<1><<<blocks, kSpmvThreads, 0, stream>>>(n_nodes, node_rowptr, node_colidx, values, x, y); break;
+    case 2: spmv_kernel<2><<<blocks, kSpmvThreads, 0, stream>>>(n_nodes, node_rowptr, node_colidx, values, x, y); break;
+    case 3: spmv_kernel<3><<<blocks, kSpmvThreads, 0, stream>>>(n_nodes, node_rowptr, node_colidx, values, x, y); break;
+    default: return FEA_ERR_INVALID;
+  }
+  return check_launch();
+}
+
+extern "C" size_t fea_pcg_workspace(int64_t n_dof) {
+  return FEA_PCG_STATE_BYTES + sizeof(double) * 2 * kMaxPartials + 3 * align_up(sizeof(double) * (size_t)n_dof, 256);
+}
+
+extern "C" int fea_pcg_init(int64_t n_dof, const double* b, const double* dinv, double* x, double* r, double* p,
+                            double tol, int32_t max_iter, void* state, void* partials, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!b || !dinv || !x || !r || !p || !state || !partials || n_dof <= 0) return FEA_ERR_INVALID;
+  FEA_TRY(check(cudaMemsetAsync(state, 0, FEA_PCG_STATE_BYTES, stream)));
+  pcg_init_kernel<<<vec_blocks(n_dof), 256, 0, stream>>>(n_dof, b, dinv, x, r, p, tol, max_iter,
+                                                        static_cast<PcgState*>(state), static_cast<double*>(partials));
+  return check_launch();
+}
+
+extern "C" int fea_pcg_step_spmv(int64_t n_owned_nodes, int32_t d, const int32_t* node_rowptr,
+                                 const int32_t* node_colidx, const double* values, const double* p, double* ap,
+                                 int64_t p_row_offset, void* state, void* partials, void* stream_) {
+  if (!node_rowptr || !node_colidx || !values || !p || !ap || !state || !partials || n_owned_nodes <= 0)
+    return FEA_ERR_INVALID;
+  FEA_TRY(step_spmv(d, n_owned_nodes, node_rowptr, node_colidx, values, p, ap, p_row_offset,
+                    static_cast<PcgState*>(state), static_cast<double*>(partials),
+                    static_cast<cudaStream_t>(stream_)));
+  return check_launch();
+}
+
+extern "C" int fea_pcg_step_update(int64_t n_dof, const double* dinv, const double* p, const double* ap, double* x,
+                                   double* r, void* state, void* partials, void* stream_) {
+  if (!dinv || !p || !ap || !x || !r || !state || !partials || n_dof <= 0) return FEA_ERR_INVALID;
+  pcg_update_kernel<<<vec_blocks(n_dof), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      n_dof, dinv, p, ap, x, r, static_cast<PcgState*>(state), static_cast<double*>(partials));
+  return check_launch();
+}
+
+extern "C" int fea_pcg_step_direction(int64_t n_dof, const double* dinv, const double* r, double* p, void* state,
+                                      double* history, void* stream_) {
+  if (!dinv || !r || !p || !state || n_dof <= 0) return FEA_ERR_INVALID;
+  pcg_direction_kernel<<<vec_blocks(n_dof), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      n_dof, dinv, r, p, static_cast<PcgState*>(state), history);
+  return check_launch();
+}
+
+extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, const int32_t* node_colidx,
+                             const double* values, const double* dinv, const double* b, double* x, double tol,
+                             int32_t max_iter, void* work, size_t work_bytes, double* history,
+                             fea_pcg_result* result_host, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!node_rowptr || !node_colidx || !values || !dinv || !b || !x || !work || !result_host) return FEA_ERR_INVALID;
+  if (n_nodes <= 0 || d < 1 || d > 3 || max_iter < 1) return FEA_ERR_INVALID;
+  const int64_t n = n_nodes * d;
+  if (work_bytes < fea_pcg_workspace(n)) return FEA_ERR_WORKSPACE;
+  PcgWork w = carve_pcg(work, n);
+
+  // two pinned snapshots of the state, polled one chunk behind the GPU
+  PcgState* snap = nullptr;
+  FEA_TRY(check(cudaMallocHost(&snap, 2 * sizeof(PcgState))));
+  cudaEvent_t ev[2];
+  int rc = FEA_OK;
+  if ((rc = check(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming))) != FEA_OK) {
+    cudaFreeHost(snap);
+    return rc;
+  }
+  if ((rc = check(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming))) != FEA_OK) {
+    cudaEventDestroy(ev[0]);
+    cudaFreeHost(snap);
+    return rc;
+  }
+
+  rc = fea_pcg_init(n, b, dinv, x, w.r, w.p, tol, max_iter, w.state, w.partials, stream);
+  const unsigned vb = vec_blocks(n);
+  const int chunk = 32;
+  int enqueued = 0, slot = 0;
+  bool pending[2] = {false, false};
+  bool finished = false;
+  while (rc == FEA_OK && !finished) {
+    const int todo = std::min(chunk, max_iter - enqueued);
+    for (int it = 0; it < todo && rc == FEA_OK; ++it) {
+      rc = step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream);
+      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials);
+      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history);
+    }
+    if (rc == FEA_OK) rc = check_launch();
+    if (rc != FEA_OK) break;
+    enqueued += todo;
+    rc = check(cudaMemcpyAsync(&snap[slot], w.state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+    if (rc != FEA_OK) break;
+    rc = check(cudaEventRecord(ev[slot], stream));
+    if (rc != FEA_OK) break;
+    pending[slot] = true;
+    const int prev = slot ^ 1;
+    if (pending[prev]) {  // look at the chunk before the one just enqueued
+      rc = check(cudaEventSynchronize(ev[prev]));
+      pending[prev] = false;
+      if (rc == FEA_OK && snap[prev].done) finished = true;
+    }
+    if (!finished && enqueued >= max_iter) {
+      rc = check(cudaEventSynchronize(ev[slot]));
+      pending[slot] = false;
+      finished = true;
+    }
+    slot ^= 1;
+  }
+  if (rc == FEA_OK) {
+    rc = check(cudaMemcpyAsync(&snap[0], w.state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+    if (rc == FEA_OK) rc = check(cudaStreamSynchronize(stream));
+  }
+  if (rc == FEA_OK) {
+    const PcgState& s = snap[0];
+    result_host->iterations = s.iter;
+    result_host->status = s.status;
+    if (!s.done && s.status == FEA_OK) result_host->status = FEA_ERR_MAXITER;
+    result_host->bnorm = std::sqrt(s.bnorm2);
+    result_host->rel_residual = s.bnorm2 > 0.0 ? std::sqrt(s.rr / s.bnorm2) : 0.0;
+  } else {
+    cudaStreamSynchronize(stream);
+  }
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  cudaFreeHost(snap);
+  return rc;
+}

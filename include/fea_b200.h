@@ -1,0 +1,249 @@
+/*
+ * fea_b200.h -- C ABI of libfea_b200.so: the B200 (sm_100a) hot path of jjrreett/fea
+ *               element stiffness -> global assembly -> solve of K u = f.
+ *
+ * The reference has no FFI of its own (it is six numpy scripts); the boundary
+ * it offers is its Python callables.  Each entry point below replaces the body of one of them
+ * and cites it (file:line in /root/reference).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends
+ *     in `_host`; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - the caller owns every buffer; the library allocates nothing persistent;
+ *   - all calls are asynchronous on `stream` unless stated otherwise;
+ *   - return value: FEA_OK or an FEA_ERR_* code for argument / launch errors.  Data-dependent
+ *     errors (detJ <= 0, PCG breakdown) are written to a caller-supplied device status slot
+ *     `int32_t status[2]`, zeroed by the caller: status[0] = code, status[1] = 0x7fffffff minus
+ *     the smallest offending element index (so that a zeroed slot needs no other initialisation).
+ *   - node coordinates: double (n_nodes, 3) row-major (cubebeam.py:45, utils.py:359);
+ *     connectivity: int32 (n_elem, nodes_per_elem) row-major, local order as the reference
+ *     (utils.py:351-353); global DOF = dof_per_node * node + component (cubebeam.py:86).
+ */
+#ifndef FEA_B200_H
+#define FEA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  FEA_OK = 0,
+  FEA_ERR_INVALID = 1,   /* bad argument (null pointer, size overflow, unsupported valence) */
+  FEA_ERR_CUDA = 2,      /* a CUDA runtime call or launch failed */
+  FEA_ERR_JACOBIAN = 3,  /* detJ <= 0 in a hex8 element (utils.py:212-215 -> ValueError) */
+  FEA_ERR_BREAKDOWN = 4, /* PCG p.Ap <= 0: K_ff not positive definite (cubebeam.py:98 -> LinAlgError) */
+  FEA_ERR_MAXITER = 5,   /* PCG hit max_iter before the tolerance */
+  FEA_ERR_WORKSPACE = 6, /* caller workspace too small */
+  FEA_ERR_DEGENERATE = 7 /* zero-length truss member */
+};
+
+/* Library / build identification ("fea_b200 <version> sm_100a"). */
+const char* fea_version(void);
+/* cudaGetLastError/cudaGetErrorString of the last failing CUDA call made by this library. */
+const char* fea_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Batched FP64 element stiffness, materialised (used by the element-level API and tests;
+ *     the assembly path below never writes Ke to HBM).
+ * ---------------------------------------------------------------------------------------- */
+
+/* hexahedral_stiffness_matrix(nodes, E, nu) -> (24,24), utils.py:127-239, batched over elements.
+ * ke: (n_elem, 24, 24) row-major.  detJ <= 0 sets status = {FEA_ERR_JACOBIAN, first element}. */
+int fea_ke_hex8(const double* nodes, const int32_t* elements, int64_t n_elem, double E, double nu,
+                double* ke, int32_t* status, void* stream);
+
+/* element_stiffness_matrix of euler_bernoulli.py:22-39 with per-element EI and length.
+ * ke: (n_elem, 4, 4). */
+int fea_ke_beam(const double* EI, const double* length, int64_t n_elem, double* ke, void* stream);
+
+/* Linearised pin-jointed member (SURVEY.md T1', tangent of truss.py:78-92 at rest):
+ * Ke = k [[cc^T, -cc^T], [-cc^T, cc^T]].  ke: (n_elem, 6, 6). */
+int fea_ke_truss(const double* nodes, const int32_t* members, const double* k, int64_t n_elem,
+                 double* ke, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2a) Symbolic assembly: connectivity -> deterministic CSR pattern.
+ *      Replaces the dense `np.zeros((ndof, ndof))` + `np.ix_` bookkeeping of cubebeam.py:80-90.
+ *      The pattern is STRUCTURAL (every (row, col) pair of every element) and equals
+ *      scipy's coo->csr + sum_duplicates + sort_indices bit for bit.
+ *
+ *      Outputs are kept at node-block level (one entry per coupled node pair) because every
+ *      DOF row of a node shares the node's column set:
+ *        row d*i+a of the DOF-level CSR = { d*j+b : j in node_colidx[node_rowptr[i]..), b<d }
+ *      and its values start at  d*d*node_rowptr[i] + a*d*cnt_i.  `fea_csr_expand` writes the
+ *      ordinary DOF-level rowptr / colidx from that.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch `fea_csr_symbolic_count` / `_fill` need. */
+size_t fea_csr_symbolic_workspace(int64_t n_nodes, int64_t n_elem, int32_t nodes_per_elem);
+
+/* Phase 1 (synchronises `stream` once to return sizes).
+ *   n2e_ptr  [n_nodes+1]            out: node -> incident (element, local node) list offsets
+ *   n2e      [n_elem*nodes_per_elem] out: entries e*nodes_per_elem + a, ascending per node
+ *   node_rowptr [n_nodes+1]         out: offsets of each node's coupled-node list
+ *   sizes_host[4]                   out (HOST): {nnz_blocks, max coupled nodes per node,
+ *                                                max incident elements per node, 0} */
+int fea_csr_symbolic_count(const int32_t* elements, int64_t n_elem, int32_t nodes_per_elem,
+                           int64_t n_nodes, int32_t* n2e_ptr, int32_t* n2e, int32_t* node_rowptr,
+                           int64_t* sizes_host, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* Phase 2: node_colidx [nnz_blocks] out, ascending within each node row. */
+int fea_csr_symbolic_fill(const int32_t* elements, int64_t n_elem, int32_t nodes_per_elem,
+                          int64_t n_nodes, const int32_t* n2e_ptr, const int32_t* n2e,
+                          const int32_t* node_rowptr, int32_t* node_colidx, int32_t max_incident,
+                          void* stream);
+
+/* DOF-level CSR arrays: rowptr [n_nodes*d + 1], colidx [d*d*nnz_blocks]. */
+int fea_csr_expand(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
+                   const int32_t* node_colidx, int32_t* rowptr, int32_t* colidx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2b) Numeric assembly, fused with element stiffness evaluation (Ke never reaches HBM) and
+ *      with Dirichlet handling.  Owner-computes: one warp owns one node's d rows, walks the
+ *      node's incident elements in ascending element order (the reference's summation order,
+ *      cubebeam.py:82-90) and writes each CSR value exactly once -- no atomics, bit-reproducible.
+ *
+ *      values  [d*d*nnz_blocks]  out, DOF-level CSR order (see 2a)
+ *      dinv    [n_nodes*d]       out, may be NULL: Jacobi preconditioner 1/K_ii, and 0 on
+ *                                constrained DOF (this is how the solver eliminates them)
+ *      fixed   [n_nodes*d] uint8 in, may be NULL: 1 = constrained (cubebeam.py:92, homogeneous)
+ *      mode    FEA_ASSEMBLE_FULL: K as assembled (needed for reactions, cubebeam.py:106)
+ *              FEA_ASSEMBLE_ELIMINATED: constrained rows/columns replaced by identity
+ * ---------------------------------------------------------------------------------------- */
+enum { FEA_ASSEMBLE_FULL = 0, FEA_ASSEMBLE_ELIMINATED = 1 };
+
+int fea_assemble_hex8(const double* nodes, const int32_t* elements, int64_t n_elem, int64_t n_nodes,
+                      double E, double nu, const int32_t* n2e_ptr, const int32_t* n2e,
+                      const int32_t* node_rowptr, const int32_t* node_colidx, int32_t max_coupled,
+                      const uint8_t* fixed, int32_t mode, double* values, double* dinv,
+                      int32_t* status, void* stream);
+
+int fea_assemble_beam(const double* EI, const double* length, const int32_t* elements,
+                      int64_t n_elem, int64_t n_nodes, const int32_t* n2e_ptr, const int32_t* n2e,
+                      const int32_t* node_rowptr, const int32_t* node_colidx, const uint8_t* fixed,
+                      int32_t mode, double* values, double* dinv, void* stream);
+
+int fea_assemble_truss(const double* nodes, const int32_t* members, const double* k, int64_t n_elem,
+                       int64_t n_nodes, const int32_t* n2e_ptr, const int32_t* n2e,
+                       const int32_t* node_rowptr, const int32_t* node_colidx, const uint8_t* fixed,
+                       int32_t mode, double* values, double* dinv, int32_t* status, void* stream);
+
+/* Scatter-add alternative for hex8 (element-parallel, FP64 atomics into `values`, which the
+ * caller zeroes): same result up to summation order; kept for comparison with the gather path. */
+int fea_assemble_hex8_scatter(const double* nodes, const int32_t* elements, int64_t n_elem,
+                              double E, double nu, const int32_t* node_rowptr,
+                              const int32_t* node_colidx, double* values, int32_t* status,
+                              void* stream);
+
+/* dinv[i] = fixed[i] ? 0 : 1 / K_ii from an assembled block-pattern matrix. */
+int fea_jacobi_dinv(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
+                    const int32_t* node_colidx, const double* values, const uint8_t* fixed,
+                    double* dinv, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Sparse matrix-vector products and the Jacobi-PCG solver (replaces np.linalg.solve,
+ *     cubebeam.py:98, fea.py:105, euler_bernoulli.py:69; and K @ u, cubebeam.py:106).
+ * ---------------------------------------------------------------------------------------- */
+
+/* y = K x on the node-block pattern (dof_per_node in {1,2,3}; 1 = ordinary CSR with
+ * node_rowptr/node_colidx = rowptr/colidx). */
+int fea_spmv(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
+             const int32_t* node_colidx, const double* values, const double* x, double* y,
+             void* stream);
+
+/* Y = K X for n_rhs right-hand sides, X and Y (n_dof, n_rhs) row-major. */
+int fea_spmm(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
+             const int32_t* node_colidx, const double* values, const double* X, double* Y,
+             int32_t n_rhs, void* stream);
+
+/* Device-resident solver state: FEA_PCG_STATE_BYTES bytes (layout below). */
+#define FEA_PCG_STATE_BYTES 256
+size_t fea_pcg_workspace(int64_t n_dof);
+
+typedef struct {
+  int32_t iterations; /* PCG iterations performed */
+  int32_t status;     /* FEA_OK, FEA_ERR_BREAKDOWN or FEA_ERR_MAXITER */
+  double rel_residual;/* recurrence ||r|| / ||b|| over free DOF at exit */
+  double bnorm;       /* ||b|| over free DOF */
+} fea_pcg_result;
+
+/* Solve K_ff u_f = f_f by Jacobi-PCG; constrained DOF are the ones with dinv == 0: their u stays 0
+ * and their rows/columns never enter (equivalent to the reference's reduced system,
+ * cubebeam.py:92-104).  x0 = 0.  Stops when ||r||_2 <= tol * ||b||_2 (recurrence residual).
+ *   b [n_dof] in; x [n_dof] out; work: fea_pcg_workspace(n_dof) bytes of device scratch;
+ *   result_host: HOST pointer (pinned preferred), filled before return (the call synchronises).
+ *   history, may be NULL: device array [max_iter] receiving ||r||/||b|| per iteration. */
+int fea_pcg_solve(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
+                  const int32_t* node_colidx, const double* values, const double* dinv,
+                  const double* b, double* x, double tol, int32_t max_iter, void* work,
+                  size_t work_bytes, double* history, fea_pcg_result* result_host, void* stream);
+
+/* The three kernels of one PCG iteration, exposed so that a multi-GPU driver can interleave its
+ * halo exchange and all-reduces.  `state` is FEA_PCG_STATE_BYTES of device memory; viewed as
+ * double[] the scalars sit at the FEA_PCG_* indices below, viewed as int32[] the counters sit at
+ * the FEA_PCG_*_I32 indices.  `partials`: 2*FEA_PCG_PARTIALS doubles of reduction scratch.
+ *   init  : x = 0, r = b on free DOF, p = dinv r;  state.rz, state.bnorm2 (local sums)
+ *   step 1: ap = K p over the owned nodes;          state.pap    = sum_owned p.ap
+ *   step 2: x += a p; r -= a ap (a = rz/pap);       state.rz_new = sum r.dinv.r; state.rr = sum_free r.r;
+ *           iteration += 1
+ *   step 3: if rr <= tol^2 bnorm2: done = 1; else p = dinv r + (rz_new/rz) p, rz = rz_new
+ * A multi-rank driver all-reduces [RZ, BNORM2] after init, [PAP] after step 1 and [RZ_NEW, RR]
+ * after step 2 (adjacent doubles).  Every step is a no-op once state.done != 0.
+ * In step 1 `p` may carry halo entries: columns index p directly, the owned rows start at node
+ * `p_row_offset` of p. */
+enum {
+  FEA_PCG_RZ = 0, FEA_PCG_BNORM2 = 1, FEA_PCG_RZ_NEW = 2, FEA_PCG_RR = 3, FEA_PCG_PAP = 4,
+  FEA_PCG_TOL2 = 5,
+  FEA_PCG_ITER_I32 = 32, FEA_PCG_DONE_I32 = 33, FEA_PCG_STATUS_I32 = 34, FEA_PCG_MAXITER_I32 = 35
+};
+#define FEA_PCG_PARTIALS 2048
+int fea_pcg_init(int64_t n_dof, const double* b, const double* dinv, double* x, double* r, double* p,
+                 double tol, int32_t max_iter, void* state, void* partials, void* stream);
+int fea_pcg_step_spmv(int64_t n_owned_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
+                      const int32_t* node_colidx, const double* values, const double* p, double* ap,
+                      int64_t p_row_offset, void* state, void* partials, void* stream);
+int fea_pcg_step_update(int64_t n_dof, const double* dinv, const double* p, const double* ap,
+                        double* x, double* r, void* state, void* partials, void* stream);
+/* history, may be NULL: device array [max_iter], entry it-1 receives ||r||/||b|| of iteration it. */
+int fea_pcg_step_direction(int64_t n_dof, const double* dinv, const double* r, double* p,
+                           void* state, double* history, void* stream);
+
+/* Batched multi-RHS Jacobi-PCG (BASELINE config 5): n_rhs <= 256 independent systems sharing K,
+ * each column with its own alpha/beta and stopping rule.  B, X: (n_dof, n_rhs) row-major.
+ * iterations_host [n_rhs] (HOST, may be NULL): iterations each column needed.
+ * result_host: iterations = total performed, rel_residual = worst column, bnorm = largest ||b_j||. */
+size_t fea_pcg_multi_workspace(int64_t n_dof, int32_t n_rhs);
+int fea_pcg_solve_multi(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
+                        const int32_t* node_colidx, const double* values, const double* dinv,
+                        const double* B, double* X, int32_t n_rhs, double tol, int32_t max_iter,
+                        void* work, size_t work_bytes, int32_t* iterations_host,
+                        fea_pcg_result* result_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) Adjacent steps of the reference scripts ("next" rows of SURVEY.md §8(f)).
+ * ---------------------------------------------------------------------------------------- */
+
+/* compute_forces(nodes, members, displaced_nodes, forces), truss.py:78-92: accumulates member
+ * forces into `forces` (n_nodes,3) IN PLACE.  k: per-member spring rate. FP64. */
+int fea_truss_member_forces(const double* nodes, const int32_t* members, const double* k,
+                            int64_t n_members, const double* displaced, double* forces, void* stream);
+
+/* moment_vector / shear_vector of euler_bernoulli.py:76-102 (the reference's own formulas). */
+int fea_beam_moment_shear(const double* u, const double* EI, const double* length, int64_t n_elem,
+                          double* moment, double* shear, void* stream);
+
+/* stack_faces_2d on device (utils.py:356-376): nodes3d (n2d*n_layers,3), elements
+ * (n_faces*(n_layers-1), 8) int32. */
+int fea_mesh_extrude(const double* nodes2d, int64_t n2d, const int32_t* faces2d, int64_t n_faces,
+                     const double* z_heights, int64_t n_layers, double* nodes3d, int32_t* elements,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEA_B200_H */

@@ -1,0 +1,395 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference-generated
+golden fixtures.  Bars (BASELINE.json north_star): CSR pattern and DOF numbering bit-exact;
+Ke / K values within 1e-10 relative; displacements within 1e-8 relative at CG residual 1e-12."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fea_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+KE_RTOL = 1e-10
+U_RTOL = 1e-8
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from fea_b200 import core, cubebeam, euler_bernoulli, fea, truss, utils
+
+    return dict(core=core, cubebeam=cubebeam, eb=euler_bernoulli, fea=fea, truss=truss, utils=utils)
+
+
+# ---------------------------------------------------------------------------------- element Ke
+def test_ke_hex8_golden(mods, golden):
+    g = golden("hex8_single.npz")
+    U = mods["utils"]
+    ke = U.hexahedral_stiffness_matrix(g["cube"], 1000, 0.0)
+    assert ke.shape == (24, 24) and ke.dtype == np.float64
+    assert rel(ke, g["ke_cube"]) < KE_RTOL
+    E, nu = float(g["E"]), float(g["nu"])
+    for x, k in zip(g["dist_nodes"], g["ke_dist"]):
+        assert rel(U.hexahedral_stiffness_matrix(x, E, nu), k) < KE_RTOL
+    # K2 round trip through the device Ke
+    f = (ke @ g["disp"].flatten()).reshape(-1, 3)
+    assert rel(f, g["f_cube"]) < 1e-10
+
+
+def test_ke_hex8_inverted_raises(mods, golden):
+    g = golden("hex8_single.npz")
+    with pytest.raises(ValueError, match="Jacobian determinant is non-positive. Check the element shape."):
+        mods["utils"].hexahedral_stiffness_matrix(g["inverted"], 1000, 0.0)
+
+
+def test_ke_hex8_batched_vs_oracle(mods):
+    rng = np.random.default_rng(2)
+    m = 1003  # not a multiple of 4: exercises the ragged last warp group
+    base = fo.HEX8_SIGNS * 0.5
+    X = base[None] * rng.uniform(0.5, 2.0, size=(m, 1, 3)) + rng.uniform(-0.2, 0.2, size=(m, 8, 3))
+    nodes = X.reshape(-1, 3)
+    elements = np.arange(8 * m).reshape(m, 8)
+    ke = mods["utils"].hexahedral_stiffness_matrices(nodes, elements, fo.E_HEX, fo.NU_HEX).cpu().numpy()
+    ref = fo.hex8_ke_batched(nodes, elements, fo.E_HEX, fo.NU_HEX)
+    err = np.abs(ke - ref).reshape(m, -1).max(axis=1) / np.abs(ref).reshape(m, -1).max(axis=1)
+    assert err.max() < KE_RTOL
+    assert np.abs(ke - ke.transpose(0, 2, 1)).max() / np.abs(ke).max() < 1e-13
+
+
+def test_ke_empty_batch(mods):
+    ke = mods["utils"].hexahedral_stiffness_matrices(np.zeros((8, 3)), np.zeros((0, 8), dtype=np.int64), 1.0, 0.3)
+    assert ke.shape == (0, 24, 24)
+
+
+def test_ke_beam_and_truss(mods, golden):
+    g = golden("euler_bernoulli.npz")
+    E, I, L, q, n, Le = g["params"]
+    ke = mods["eb"].beam_stiffness_matrices(E * I, Le)[0].cpu().numpy()
+    assert rel(ke, g["element_stiffness_matrix"]) < KE_RTOL
+    rng = np.random.default_rng(3)
+    EI, Ls = rng.uniform(1e3, 1e6, 77), rng.uniform(0.01, 2.0, 77)
+    assert rel(mods["eb"].beam_stiffness_matrices(EI, Ls).cpu().numpy(), fo.beam_ke_batched(EI, Ls)) < KE_RTOL
+    nodes, members, k, _, _ = fo.lattice_truss_case(4, 1)
+    kt = mods["truss"].member_stiffness_matrices(nodes, members, k).cpu().numpy()
+    assert rel(kt, fo.truss_ke_batched(nodes, members, k)) < KE_RTOL
+    # tangent of the reference's compute_forces (finite differences, golden)
+    t = golden("truss.npz")
+    n64 = t["nodes"].astype(np.float64)
+    kk = mods["truss"].member_stiffness_matrices(n64, t["members"], np.full(2, float(t["stiffness"]))).cpu().numpy()
+    K = fo.assemble_csr(t["members"], kk, 3, 3).toarray()
+    assert np.abs(K - t["tangent_fd"]).max() < 1e-4
+
+
+# ------------------------------------------------------------------------ symbolic + numeric
+def _hex_cases():
+    yield "cantilever 6x3x3", fo.cantilever_case(6, 3)
+    yield "shipped cubebeam", fo.cubebeam_case()
+    yield "shipped tube (periodic section)", fo.tube_case()
+    yield "single element", fo.cantilever_case(1, 1)
+    # distorted + shuffled element order + an unreferenced node
+    nodes, elements, cons, forces = fo.cantilever_case(5, 4)
+    rng = np.random.default_rng(7)
+    h = 0.1 / 4
+    nodes = nodes + rng.uniform(-0.2 * h, 0.2 * h, size=nodes.shape)
+    elements = elements[rng.permutation(elements.shape[0])]
+    nodes = np.vstack([nodes, [[9.0, 9.0, 9.0]]])
+    cons = np.vstack([cons, [[1, 1, 1]]])
+    forces = np.vstack([forces, [[0.0, 0.0, 0.0]]])
+    yield "distorted, shuffled, isolated node", (nodes, elements, cons, forces)
+
+
+@pytest.mark.parametrize("name,case", list(_hex_cases()), ids=[n for n, _ in _hex_cases()])
+def test_hex8_pattern_and_values(mods, name, case):
+    core = mods["core"]
+    nodes, elements, cons, forces = case
+    nd = core.to_device(nodes, torch.float64)
+    el = core.to_device(elements, torch.int32)
+    pat = core.symbolic(el, nodes.shape[0])
+    rowptr, colidx = (t.cpu().numpy() for t in pat.csr(3))
+    Kref = fo.assemble_csr(elements, fo.hex8_ke_batched(nodes, elements, fo.E_HEX, fo.NU_HEX), nodes.shape[0], 3)
+    indptr, indices = fo.structural_pattern(elements, nodes.shape[0], 3)
+    # bit-exact pattern and DOF numbering
+    assert rowptr.dtype == np.int32 and colidx.dtype == np.int32
+    assert np.array_equal(rowptr, indptr) and np.array_equal(colidx, indices)
+    assert np.array_equal(rowptr, Kref.indptr) and np.array_equal(colidx, Kref.indices)
+    K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, pattern=pat)
+    vals = K.values.cpu().numpy()
+    assert np.abs(vals - Kref.data).max() / np.abs(Kref.data).max() < KE_RTOL
+    # deterministic: a second assembly is bit-identical
+    K2 = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, pattern=pat)
+    assert torch.equal(K.values, K2.values)
+    # the atomics scatter-add variant agrees to rounding
+    from fea_b200 import _lib
+
+    lib = _lib.load()
+    vs = torch.zeros_like(K.values)
+    st = torch.zeros(2, dtype=torch.int32, device=vs.device)
+    rc = lib.fea_assemble_hex8_scatter(nd.data_ptr(), el.data_ptr(), el.shape[0], fo.E_HEX, fo.NU_HEX,
+                                       pat.node_rowptr.data_ptr(), pat.node_colidx.data_ptr(), vs.data_ptr(),
+                                       st.data_ptr(), None)
+    assert rc == 0 and int(st[0]) == 0
+    assert np.abs(vs.cpu().numpy() - Kref.data).max() / np.abs(Kref.data).max() < KE_RTOL
+    # Dirichlet: dinv encodes the constraints; eliminated mode = identity rows/cols
+    fixed = core._fixed_mask(cons, nodes.size)
+    Kf = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, pattern=pat, fixed=fixed)
+    dinv = Kf.dinv.cpu().numpy()
+    diag = Kref.diagonal()
+    free = fo.free_dofs(cons)
+    isfree = np.zeros(nodes.size, bool)
+    isfree[free] = True
+    isfree &= diag != 0
+    assert np.all(dinv[~isfree] == 0.0)
+    assert rel(dinv[isfree], 1.0 / diag[isfree]) < KE_RTOL
+    Ke = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, pattern=pat, fixed=fixed, mode=_lib.ASSEMBLE_ELIMINATED)
+    Ke = Ke.to_scipy()
+    sub = Ke[free][:, free]
+    assert np.abs(sub - Kref[free][:, free]).max() / np.abs(Kref.data).max() < KE_RTOL
+    fx = np.setdiff1d(np.arange(nodes.size), free)
+    fx = fx[diag[fx] != 0]
+    assert np.abs(Ke[fx][:, free]).max() == 0 and np.abs(Ke[free][:, fx]).max() == 0
+    assert np.array_equal(Ke[fx][:, fx].diagonal(), np.ones(fx.size))
+
+
+def test_inverted_element_in_assembly_raises(mods):
+    nodes, elements, cons, forces = fo.cantilever_case(3, 2)
+    elements = elements.copy()
+    elements[5] = elements[5][[4, 5, 6, 7, 0, 1, 2, 3]]
+    with pytest.raises(ValueError, match="Jacobian determinant is non-positive") as exc:
+        mods["cubebeam"].solve(nodes, elements, cons, forces)
+    assert exc.value.element == 5
+
+
+def test_bad_connectivity_rejected(mods):
+    nodes, elements, cons, forces = fo.cantilever_case(2, 1)
+    elements = elements.copy()
+    elements[0, 0] = nodes.shape[0] + 5
+    with pytest.raises(ValueError):
+        mods["cubebeam"].solve(nodes, elements, cons, forces)
+
+
+def test_beam_and_truss_assembly(mods):
+    core = mods["core"]
+    elements, EI, Ls, cons, loads = fo.beam_cantilever_case(257)
+    rng = np.random.default_rng(4)
+    EI = EI * rng.uniform(0.5, 2.0, EI.shape)
+    Ls = Ls * rng.uniform(0.5, 2.0, Ls.shape)
+    K = core.assemble_beam(core.to_device(EI, torch.float64), core.to_device(Ls, torch.float64),
+                           core.to_device(elements, torch.int32), 258)
+    Kref = fo.assemble_csr(elements, fo.beam_ke_batched(EI, Ls), 258, 2)
+    rp, ci = (t.cpu().numpy() for t in K.pattern.csr(2))
+    assert np.array_equal(rp, Kref.indptr) and np.array_equal(ci, Kref.indices)
+    assert rel(K.values.cpu().numpy(), Kref.data) < KE_RTOL
+    assert K.nnz == 4 * (3 * 258 - 2)
+
+    nodes, members, k, cons, loads = fo.lattice_truss_case(6, 2)
+    perm = np.random.default_rng(5).permutation(members.shape[0])
+    members, k = members[perm], k[perm]
+    K = core.assemble_truss(core.to_device(nodes, torch.float64), core.to_device(members, torch.int32),
+                            core.to_device(k, torch.float64))
+    Kref = fo.assemble_csr(members, fo.truss_ke_batched(nodes, members, k), nodes.shape[0], 3)
+    rp, ci = (t.cpu().numpy() for t in K.pattern.csr(3))
+    assert np.array_equal(rp, Kref.indptr) and np.array_equal(ci, Kref.indices)
+    assert np.abs(K.values.cpu().numpy() - Kref.data).max() / np.abs(Kref.data).max() < KE_RTOL
+
+
+# --------------------------------------------------------------------------------- SpMV / PCG
+def test_spmv_spmm_vs_scipy(mods):
+    core = mods["core"]
+    nodes, elements, cons, forces = fo.cantilever_case(9, 4)
+    K = core.assemble_hex8(core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32), 1.0, 0.3)
+    Kref = K.to_scipy()
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal(K.n_dof)
+    y = K.matvec(core.to_device(x, torch.float64)).cpu().numpy()
+    assert rel(y, Kref @ x) < 1e-13
+    for r in (1, 3, 32, 64, 70):
+        X = rng.standard_normal((K.n_dof, r))
+        Y = K.matmat(core.to_device(X, torch.float64)).cpu().numpy()
+        assert rel(Y, Kref @ X) < 1e-13
+    # D = 1: the same kernel as a plain CSR SpMV on the DOF-level arrays
+    from fea_b200 import _lib
+
+    rowptr, colidx = K.pattern.csr(3)
+    y1 = torch.empty(K.n_dof, dtype=torch.float64, device="cuda")
+    xd = core.to_device(x, torch.float64)
+    rc = _lib.load().fea_spmv(K.n_dof, 1, rowptr.data_ptr(), colidx.data_ptr(), K.values.data_ptr(), xd.data_ptr(),
+                              y1.data_ptr(), None)
+    assert rc == 0
+    assert rel(y1.cpu().numpy(), Kref @ x) < 1e-13
+    # rigid translations are in the null space of the unconstrained K (row sums vanish)
+    t = np.tile([1.0, 0.0, 0.0], nodes.shape[0])
+    assert np.abs(K.matvec(core.to_device(t, torch.float64)).cpu().numpy()).max() < 1e-12 * np.abs(Kref.data).max()
+
+
+def test_pcg_vs_oracle(mods):
+    core = mods["core"]
+    nodes, elements, cons, forces = fo.cantilever_case(20, 4)
+    nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
+    fixed = core._fixed_mask(cons, nodes.size)
+    K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, fixed=fixed)
+    u, info = core.pcg(K, core.to_device(forces, torch.float64).reshape(-1), tol=1e-12, history=True)
+    uo, fo_, io = fo.solve_hex8(nodes, elements, cons, forces, method="pcg", tol=1e-12)
+    ud, _, _ = fo.solve_hex8(nodes, elements, cons, forces, method="direct")
+    assert info.status == 0 and info.rel_residual <= 1e-12
+    assert abs(info.iterations - io["iterations"]) <= max(5, io["iterations"] // 50)
+    assert rel(u.cpu().numpy(), uo.ravel()) < U_RTOL
+    assert rel(u.cpu().numpy(), ud.ravel()) < U_RTOL
+    # same recurrence: early residual history tracks the oracle's
+    h, ho = info.history, np.array(io["history"])
+    k = min(40, len(h), len(ho))
+    assert np.allclose(h[:k], ho[:k], rtol=1e-6)
+    assert np.all(u.cpu().numpy()[cons.ravel() != 0] == 0.0)
+
+
+def test_pcg_zero_rhs_and_singular(mods):
+    core = mods["core"]
+    nodes, elements, cons, forces = fo.cantilever_case(3, 2)
+    u, f = mods["cubebeam"].solve(nodes, elements, cons, np.zeros_like(forces))
+    assert np.all(u == 0) and np.all(f == 0)
+    # unconstrained body: the reference's np.linalg.solve raises LinAlgError (singular K)
+    with pytest.raises(np.linalg.LinAlgError):
+        from fea_b200 import model
+
+        model.solve_hex8(nodes, elements, np.zeros_like(cons), forces, max_iter=2000)
+
+
+# ---------------------------------------------------------------- end-to-end, reference surface
+def test_k5_cubebeam_shipped(mods, golden):
+    g = golden("cubebeam.npz")
+    nodes, elements, cons, forces = mods["cubebeam"].shipped_case()
+    before = (nodes.copy(), elements.copy(), cons.copy(), forces.copy())
+    u, f = mods["cubebeam"].solve(nodes, elements, cons, forces)
+    assert u.shape == nodes.shape and f.shape == nodes.shape and u.dtype == np.float64
+    for a, b in zip((nodes, elements, cons, forces), before):
+        assert np.array_equal(a, b)  # inputs untouched (cubebeam.py:102-108)
+    assert rel(u, g["displacements"]) < U_RTOL
+    assert rel(f, g["forces_out"]) < 1e-7
+    assert abs(np.abs(u).max() - 3.050405508343811e-04) < 1e-11
+    assert abs(f[nodes[:, 2] == 0][:, 1].sum() + 1402.158792651803) < 1e-5
+
+
+def test_k6_tube_shipped(mods, golden):
+    g = golden("fea_tube.npz")
+    nodes, elements, cons, forces = mods["fea"].shipped_case()
+    u, f = mods["fea"].solve(nodes, elements, cons, forces)
+    assert rel(u, g["displacements"]) < U_RTOL
+    assert rel(f, g["forces_out"]) < 1e-7
+
+
+def test_k7_euler_bernoulli(mods, golden):
+    g = golden("euler_bernoulli.npz")
+    eb = mods["eb"]
+    res = eb.run()
+    assert rel(res["global_stiffness_matrix"], g["global_stiffness_matrix"]) < KE_RTOL
+    assert np.array_equal(res["load_vector"], g["load_vector"])
+    assert res["fixed_dofs"] == list(g["fixed_dofs"]) and res["free_dofs"] == list(g["free_dofs"])
+    assert rel(res["displacement_vector"], g["displacement_vector"]) < 1e-7  # cond(K) ~ 5e8, SURVEY H3
+    m, v = eb.moment_shear(g["displacement_vector"], np.full(100, eb.E * eb.I), np.full(100, eb.element_length))
+    assert rel(m, g["moment_vector"]) < 1e-12 and rel(v, g["shear_vector"]) < 1e-12
+    assert eb.displacement_vector is res["displacement_vector"]  # lazy module attribute
+    # cantilever, n = 100: against the oracle's direct solve and the analytic tip deflection
+    el, EI, Ls, cons, loads = eb.cantilever_case(100)
+    u = eb.solve_beam(el, EI, Ls, cons, loads)
+    uo, _, _ = fo.solve_beam(el, EI, Ls, cons, loads, method="direct")
+    assert rel(u, uo) < 1e-6
+    assert abs(u[-1, 0] - (-1000.0) / (3 * 210e9 * 1e-6)) < 1e-8
+
+
+def test_k8_truss(mods, golden):
+    g = golden("truss.npz")
+    T = mods["truss"]
+    n64 = g["nodes"].astype(np.float64)
+    f = np.zeros_like(n64)
+    assert T.compute_forces(n64, g["members"], g["probe"], f) is None
+    assert rel(f, g["f_probe"]) < 1e-13
+    f += 1.0  # accumulates in place
+    T.compute_forces(n64, g["members"], g["probe"], f)
+    assert rel(f, 2 * g["f_probe"] + 1.0) < 1e-13
+    disp, hist = T.relax(T.nodes, T.members, T.loads, 40)
+    assert disp.dtype == np.float32
+    assert np.allclose(hist, g["residual_history"], rtol=2e-3, atol=2e-4)  # float32 script vs FP64 kernel
+    assert np.allclose(disp, g["displaced_history"][-1], atol=1e-5)
+    u, K, info = T.solve_linear(*T.shipped_case(), return_matrix=True)
+    assert np.allclose(u[2], [0.0, -0.25, 0.0], atol=1e-14)
+
+
+def test_truss_lattice_multi_rhs(mods):
+    T = mods["truss"]
+    nodes, members, k, cons, loads = fo.lattice_truss_case(7, 64)
+    X, K, info = T.solve_linear(nodes, members, k, cons, loads, return_matrix=True)
+    Kref = fo.assemble_csr(members, fo.truss_ke_batched(nodes, members, k), nodes.shape[0], 3)
+    free = fo.free_dofs(cons)
+    import scipy.sparse.linalg as spla
+
+    Xd = spla.splu(Kref[free][:, free].tocsc()).solve(loads[free])
+    assert rel(X[free], Xd) < U_RTOL
+    assert np.all(X[np.setdiff1d(np.arange(loads.shape[0]), free)] == 0)
+    Xo, iters = fo.jacobi_pcg_multi(Kref[free][:, free].tocsr(), loads[free], tol=1e-12)
+    assert np.abs(info.history - iters).max() <= 5  # per-column iteration counts track the oracle
+    assert info.rel_residual <= 1e-12
+    # single RHS through the same entry point
+    u1 = T.solve_linear(nodes, members, k, cons, loads[:, 0].reshape(-1, 3))
+    assert rel(u1.ravel(), X[:, 0]) < 1e-9
+
+
+def test_mesh_extrude_device(mods):
+    U, C = mods["utils"], mods["cubebeam"]
+    n2, q2 = C.generate_quad_grid(5, 3, 0.3, 0.2)
+    z = np.linspace(0, 2, 9)
+    nh, eh = U.stack_faces_2d(n2, q2, z)
+    nd, ed = U.stack_faces_2d_device(n2, q2, z)
+    assert np.array_equal(nd.cpu().numpy(), nh) and np.array_equal(ed.cpu().numpy(), eh)
+
+
+# ------------------------------------------------------- full-size, size-independent properties
+def test_config3_full_size_properties(mods):
+    """BASELINE config 3 (100x20x20, 133,623 DOF): pattern counts, equilibrium, symmetry of the
+    response, true residual -- no oracle run needed at this size."""
+    core, C = mods["core"], mods["cubebeam"]
+    from fea_b200 import model
+
+    nodes, elements, cons, forces = C.cantilever_case(100, 20)
+    u, f, info, K = model.solve_hex8(nodes, elements, cons, forces, return_info=True)
+    assert K.nnz == 10_080_189 and K.n_dof == 133_623
+    assert info.status == 0 and info.rel_residual <= 1e-12 and 1500 < info.iterations < 3000
+    free = cons.ravel() == 0
+    # nodal forces on free DOF reproduce the applied loads; reactions balance them (quirk Q2)
+    assert np.abs(f.ravel()[free] - forces.ravel()[free]).max() < 1e-8 * np.abs(forces).max()
+    applied = forces.ravel()[free].reshape(-1)
+    assert abs(f[nodes[:, 2] == 0][:, 1].sum() + forces[nodes[:, 2] != 0][:, 1].sum()) < 1e-6 * abs(applied.sum())
+    # mirror symmetry about the plane x = width/2 of a y-load: u_y(x) = u_y(w - x), u_x antisymmetric
+    grid = u.reshape(101, 21, 21, 3)
+    assert np.abs(grid[..., 1] - grid[:, :, ::-1, 1]).max() < 1e-9 * np.abs(u).max()
+    assert np.abs(grid[..., 0] + grid[:, :, ::-1, 0]).max() < 1e-9 * np.abs(u).max()
+    # Euler-Bernoulli tip deflection of the equivalent beam within a few percent
+    total = forces[:, 1].sum() - forces[nodes[:, 2] == 0][:, 1].sum()
+    w_tip = grid[-1, :, :, 1].mean()
+    EI = fo.E_HEX * 0.1**4 / 12
+    assert 0.9 < w_tip / (total * 1.0**3 / (8 * EI)) < 1.15  # uniformly distributed load along z
+
+
+def test_config4_assembly_properties(mods):
+    """BASELINE config 4 (400x80x80, 7.9 M DOF) assembled on one GPU: structural nnz, null space,
+    SpMV linearity and symmetry <Kx, y> = <x, Ky>."""
+    core, C, U = mods["core"], mods["cubebeam"], mods["utils"]
+    n2, q2 = C.generate_quad_grid(80, 80, 0.1, 0.1)
+    nd, el = U.stack_faces_2d_device(n2, q2, np.linspace(0, 1.0, 401))
+    K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX)
+    assert K.n_dof == 7_892_883 and K.nnz == 627_797_529
+    scale = float(K.values.abs().max())
+    for c in range(3):
+        t = torch.zeros(K.n_dof, dtype=torch.float64, device="cuda")
+        t[c::3] = 1.0
+        assert float(K.matvec(t).abs().max()) < 1e-11 * scale
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(K.n_dof, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.randn(K.n_dof, dtype=torch.float64, device="cuda", generator=g)
+    Kx, Ky = K.matvec(x), K.matvec(y)
+    assert abs(float(Kx @ y - x @ Ky)) < 1e-10 * abs(float(Kx @ y))
+    z = K.matvec(2.0 * x - 3.0 * y)
+    assert float((z - (2.0 * Kx - 3.0 * Ky)).abs().max()) < 1e-12 * float(Kx.abs().max())
+    assert float(x @ Kx) > 0
