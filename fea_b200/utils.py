@@ -17,6 +17,8 @@ def hexahedral_stiffness_matrices(nodes, elements, E: float, nu: float) -> torch
         raise ValueError("elements must be (M, 8)")
     m = elements_d.shape[0]
     ke = torch.empty((m, 24, 24), dtype=torch.float64, device=nodes_d.device)
+    if m == 0:
+        return ke
     status = core._status_slot()
     _lib.check(lib.fea_ke_hex8(nodes_d.data_ptr(), elements_d.data_ptr(), m, float(E), float(nu), ke.data_ptr(),
                                status.data_ptr(), core._stream()), "fea_ke_hex8")
