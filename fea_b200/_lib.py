@@ -29,7 +29,7 @@ ASSEMBLE_ELIMINATED = 1
 PCG_STATE_BYTES = 256
 PCG_PARTIALS = 2048
 # double indices into the state
-PCG_RZ, PCG_BNORM2, PCG_RZ_NEW, PCG_RR, PCG_PAP, PCG_TOL2 = 0, 1, 2, 3, 4, 5
+PCG_RZ, PCG_BNORM2, PCG_RZ_NEW, PCG_RR, PCG_PAP, PCG_TOL2, PCG_RR_FINAL = 0, 1, 2, 3, 4, 5, 6
 # int32 indices into the state
 PCG_ITER_I32, PCG_DONE_I32, PCG_STATUS_I32, PCG_MAXITER_I32 = 32, 33, 34, 35
 
@@ -51,6 +51,8 @@ P = c_void_p  # every device / host pointer crosses the ABI as a plain address
 PROTOTYPES = {
     "fea_version": (c_char_p, []),
     "fea_last_cuda_error": (c_char_p, []),
+    "fea_profile_enable": (None, [c_int32]),
+    "fea_profile_read": (None, [P]),
     "fea_ke_hex8": (c_int32, [P, P, c_int64, c_double, c_double, P, P, P]),
     "fea_ke_beam": (c_int32, [P, P, c_int64, P, P]),
     "fea_ke_truss": (c_int32, [P, P, P, c_int64, P, P, P]),

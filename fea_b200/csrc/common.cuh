@@ -13,7 +13,20 @@ constexpr unsigned kFull = 0xffffffffu;
 // Last CUDA error seen by any entry point (reported by fea_last_cuda_error()).
 void set_last_error(cudaError_t e);
 
-inline int check_launch() {
+// Profiling counters (read through fea_profile_read): kernels launched by this library, and a
+// sampled CUDA-event timing of the PCG SpMV kernel taken inside fea_pcg_solve.
+struct Profile {
+  long long launches;
+  int enabled;
+  long long spmv_samples;
+  double spmv_ms;
+  long long pcg_iterations;
+};
+Profile& profile();
+
+// Checks the launch(es) just made and counts them (n = kernels launched since the last check).
+inline int check_launch(int n = 1) {
+  profile().launches += n;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error(e);

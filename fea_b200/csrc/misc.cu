@@ -10,6 +10,9 @@
 namespace fea {
 
 static char g_err[256] = "";
+static Profile g_profile = {0, 0, 0, 0.0, 0};
+
+Profile& profile() { return g_profile; }
 
 void set_last_error(cudaError_t e) {
   std::snprintf(g_err, sizeof(g_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -129,6 +132,21 @@ using namespace fea;
 
 extern "C" const char* fea_version(void) { return "fea_b200 0.1.0 sm_100a"; }
 extern "C" const char* fea_last_cuda_error(void) { return g_err; }
+
+extern "C" void fea_profile_enable(int32_t enable) {
+  g_profile.enabled = enable;
+  g_profile.launches = 0;
+  g_profile.spmv_samples = 0;
+  g_profile.spmv_ms = 0.0;
+  g_profile.pcg_iterations = 0;
+}
+
+extern "C" void fea_profile_read(double* out_host) {
+  out_host[0] = (double)g_profile.launches;
+  out_host[1] = (double)g_profile.spmv_samples;
+  out_host[2] = g_profile.spmv_ms;
+  out_host[3] = (double)g_profile.pcg_iterations;
+}
 
 template <int D>
 static int launch_spmm(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values, const double* X,

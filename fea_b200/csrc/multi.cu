@@ -426,7 +426,7 @@ extern "C" int fea_pcg_solve_multi(int64_t n_nodes, int32_t d, const int32_t* no
       multi_update_kernel<<<vb, block, 0, stream>>>(n, R, dinv, w.P, w.AP, X, w.Rv, w);
       multi_direction_kernel<<<vb, block, 0, stream>>>(n, R, dinv, w.Rv, w.P, w);
     }
-    rc = check_launch();
+    rc = check_launch(3 * todo);
     if (rc != FEA_OK) break;
     enqueued += todo;
     rc = check(cudaMemcpyAsync(&snap[slot], w.st, sizeof(MultiState), cudaMemcpyDeviceToHost, stream));

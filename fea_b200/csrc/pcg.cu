@@ -32,7 +32,9 @@ struct PcgState {
   double rr;       // FEA_PCG_RR      ||r||^2 over free DOF
   double pap;      // FEA_PCG_PAP
   double tol2;     // FEA_PCG_TOL2
-  double spare[10];
+  double rr_final; // FEA_PCG_RR_FINAL  ||r||^2 frozen when `done` is set (later no-op steps of a
+                   //                   multi-rank driver keep all-reducing the live scalars)
+  double spare[9];
   int32_t iter;      // int32 index 32
   int32_t done;      // 33
   int32_t status;    // 34
@@ -131,6 +133,7 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       st->done = 1;
       st->status = st->bnorm2 == 0.0 ? FEA_OK : FEA_ERR_BREAKDOWN;
+      st->rr_final = st->rr;
     }
     return;
   }
@@ -188,11 +191,13 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
       history[st->iter - 1] = sqrt(st->rr / st->bnorm2);
     if (converged) {
       st->done = 1;
+      st->rr_final = st->rr;
     } else {
       st->rz = rz_new;
       if (st->iter >= st->max_iter) {
         st->done = 1;
         st->status = FEA_ERR_MAXITER;
+        st->rr_final = st->rr;
       }
     }
     st->counter[2] = 0;
@@ -382,14 +387,25 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   int enqueued = 0, slot = 0;
   bool pending[2] = {false, false};
   bool finished = false;
+  // measurement hook: CUDA-event pairs around the first SpMV launch of each chunk
+  constexpr int kMaxSamples = 256;
+  cudaEvent_t* sample_ev = nullptr;
+  int n_samples = 0;
+  if (profile().enabled) {
+    sample_ev = new cudaEvent_t[2 * kMaxSamples];
+    for (int i = 0; i < 2 * kMaxSamples; ++i) cudaEventCreate(&sample_ev[i]);
+  }
   while (rc == FEA_OK && !finished) {
     const int todo = std::min(chunk, max_iter - enqueued);
     for (int it = 0; it < todo && rc == FEA_OK; ++it) {
+      const bool sample = sample_ev != nullptr && it == 0 && n_samples < kMaxSamples;
+      if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
       rc = step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream);
+      if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
       pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials);
       pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history);
     }
-    if (rc == FEA_OK) rc = check_launch();
+    if (rc == FEA_OK) rc = check_launch(3 * todo);
     if (rc != FEA_OK) break;
     enqueued += todo;
     rc = check(cudaMemcpyAsync(&snap[slot], w.state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
@@ -421,8 +437,21 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     if (!s.done && s.status == FEA_OK) result_host->status = FEA_ERR_MAXITER;
     result_host->bnorm = std::sqrt(s.bnorm2);
     result_host->rel_residual = s.bnorm2 > 0.0 ? std::sqrt(s.rr / s.bnorm2) : 0.0;
+    profile().pcg_iterations += s.iter;
+    for (int i = 0; i < n_samples; ++i) {
+      if (i * chunk >= s.iter) break;  // launches after convergence are no-ops: not SpMV work
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sample_ev[2 * i], sample_ev[2 * i + 1]) == cudaSuccess) {
+        profile().spmv_ms += ms;
+        profile().spmv_samples += 1;
+      }
+    }
   } else {
     cudaStreamSynchronize(stream);
+  }
+  if (sample_ev != nullptr) {
+    for (int i = 0; i < 2 * kMaxSamples; ++i) cudaEventDestroy(sample_ev[i]);
+    delete[] sample_ev;
   }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);

@@ -146,7 +146,7 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* bloc
   scan_reduce_kernel<<<nb, kScanThreads, 0, stream>>>(in, n, block_sums, max_out);
   scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, nb);
   scan_apply_kernel<<<nb, kScanThreads, 0, stream>>>(in, out, n, block_sums, nb);
-  return check_launch();
+  return check_launch(3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -358,7 +358,7 @@ extern "C" int fea_csr_symbolic_count(const int32_t* elements, int64_t n_elem, i
   if (total > 0) {
     incidence_fill_kernel<<<blocks, threads, 0, stream>>>(elements, total, w.cursor, n2e);
     incidence_sort_kernel<<<(unsigned)ceil_div(n_nodes, 128), 128, 0, stream>>>(n2e_ptr, n2e, n_nodes);
-    FEA_TRY(check_launch());
+    FEA_TRY(check_launch(2));
   }
   // unique coupled-node count per node, then scan in place
   FEA_TRY(launch_neighbors(false, elements, nodes_per_elem, n_nodes, n2e_ptr, n2e, std::max(max_incident, 1), nullptr,

@@ -46,6 +46,14 @@ const char* fea_version(void);
 /* cudaGetLastError/cudaGetErrorString of the last failing CUDA call made by this library. */
 const char* fea_last_cuda_error(void);
 
+/* Measurement hooks (bench.py).  fea_profile_enable(1) zeroes the counters and makes
+ * fea_pcg_solve time a sample of its SpMV launches with CUDA events on the solve's own stream
+ * (one launch per 32-iteration chunk, at most 256 per solve).  fea_profile_read fills
+ * out_host[4] (HOST) = {kernels launched by the library, SpMV launches timed, sum of their
+ * durations in ms, PCG iterations executed}. */
+void fea_profile_enable(int32_t enable);
+void fea_profile_read(double* out_host);
+
 /* ------------------------------------------------------------------------------------------
  * (1) Batched FP64 element stiffness, materialised (used by the element-level API and tests;
  *     the assembly path below never writes Ke to HBM).
@@ -198,7 +206,7 @@ int fea_pcg_solve(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_row
  * `p_row_offset` of p. */
 enum {
   FEA_PCG_RZ = 0, FEA_PCG_BNORM2 = 1, FEA_PCG_RZ_NEW = 2, FEA_PCG_RR = 3, FEA_PCG_PAP = 4,
-  FEA_PCG_TOL2 = 5,
+  FEA_PCG_TOL2 = 5, FEA_PCG_RR_FINAL = 6 /* ||r||^2 frozen at the moment `done` was set */,
   FEA_PCG_ITER_I32 = 32, FEA_PCG_DONE_I32 = 33, FEA_PCG_STATUS_I32 = 34, FEA_PCG_MAXITER_I32 = 35
 };
 #define FEA_PCG_PARTIALS 2048
