@@ -66,13 +66,13 @@ PROTOTYPES = {
     "fea_assemble_truss": (c_int32, [P, P, P, c_int64, c_int64, P, P, P, P, P, c_int32, P, P, P, P]),
     "fea_assemble_hex8_scatter": (c_int32, [P, P, c_int64, c_double, c_double, P, P, P, P, P]),
     "fea_jacobi_dinv": (c_int32, [c_int64, c_int32, P, P, P, P, P, P]),
-    "fea_spmv": (c_int32, [c_int64, c_int32, P, P, P, P, P, P]),
+    "fea_spmv": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, P]),
     "fea_spmm": (c_int32, [c_int64, c_int32, P, P, P, P, P, c_int32, P]),
     "fea_pcg_workspace": (c_size_t, [c_int64]),
-    "fea_pcg_solve": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, c_double, c_int32, P, c_size_t, P,
+    "fea_pcg_solve": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, P, c_double, c_int32, P, c_size_t, P,
                                 ctypes.POINTER(PcgResult), P]),
     "fea_pcg_init": (c_int32, [c_int64, P, P, P, P, P, c_double, c_int32, P, P, P]),
-    "fea_pcg_step_spmv": (c_int32, [c_int64, c_int32, P, P, P, P, P, c_int64, P, P, P]),
+    "fea_pcg_step_spmv": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, c_int64, P, P, P]),
     "fea_pcg_step_update": (c_int32, [c_int64, P, P, P, P, P, P, P, P]),
     "fea_pcg_step_direction": (c_int32, [c_int64, P, P, P, P, P, P]),
     "fea_pcg_multi_workspace": (c_size_t, [c_int64, c_int32]),

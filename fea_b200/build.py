@@ -48,7 +48,8 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     nvcc = find_nvcc()
     sources = [s for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
-    common_deps = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(INCLUDE, "fea_b200.h"), __file__]
+    headers = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    common_deps = [os.path.join(CSRC, h) for h in headers] + [os.path.join(INCLUDE, "fea_b200.h"), __file__]
     objs, jobs = [], []
     for src in sources:
         src_path = os.path.join(CSRC, src)

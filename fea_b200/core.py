@@ -140,7 +140,7 @@ class BlockCSR:
         y = torch.empty(self.n_dof, dtype=torch.float64, device=x.device) if out is None else out
         pt = self.pattern
         _lib.check(lib.fea_spmv(pt.n_nodes, self.dof_per_node, _p(pt.node_rowptr), _p(pt.node_colidx),
-                                _p(self.values), _p(x), _p(y), _stream()), "fea_spmv")
+                                _p(self.values), pt.max_coupled, _p(x), _p(y), _stream()), "fea_spmv")
         return y
 
     def matmat(self, X: torch.Tensor) -> torch.Tensor:
@@ -259,6 +259,7 @@ def pcg(A: BlockCSR, b: torch.Tensor, tol: float = 1e-12, max_iter: int | None =
     res = _lib.PcgResult()
     pt = A.pattern
     _lib.check(lib.fea_pcg_solve(pt.n_nodes, A.dof_per_node, _p(pt.node_rowptr), _p(pt.node_colidx), _p(A.values),
+                                 pt.max_coupled,
                                  _p(A.dinv), _p(b), _p(x), float(tol), int(max_iter), _p(work), ws_bytes, _p(hist),
                                  ctypes.byref(res), _stream()), "fea_pcg_solve")
     info = SolveInfo(res.iterations, res.rel_residual, res.bnorm, res.status,

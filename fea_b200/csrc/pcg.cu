@@ -20,9 +20,32 @@
 #include <algorithm>
 #include <cmath>
 
-#include "spmv.cuh"
+#include "spmv_tma.cuh"
 
 namespace fea {
+
+TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_colidx, int64_t n_nodes) {
+  static int sm_count = 0, smem_optin = 0;
+  TmaPlan plan;
+  plan.ok = false;
+  plan.grid = 0;
+  plan.layout = TmaLayout{0, 0, 0, 0};
+  if (max_coupled < 1 || d < 1 || d > 3) return plan;
+  if ((reinterpret_cast<uintptr_t>(values) & 15u) || (reinterpret_cast<uintptr_t>(node_colidx) & 15u)) return plan;
+  if (sm_count == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return plan;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  if (sm_count <= 0 || smem_optin <= 0) return plan;
+  plan.layout = tma_layout(d, max_coupled, (size_t)smem_optin - 1024);  // static smem of the reducing kernels
+  if (plan.layout.stages < 2) return plan;
+  const int64_t tiles = ceil_div(n_nodes, kTileNodes);
+  plan.grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, sm_count));
+  plan.ok = true;
+  return plan;
+}
 
 // Device-resident solver state (FEA_PCG_STATE_BYTES = 256 bytes).
 struct PcgState {
@@ -118,6 +141,59 @@ pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const 
       st->pap = s;
       st->counter[0] = 0;
     }
+  }
+}
+
+// step 1, bulk-copy pipeline variant (spmv_tma.cuh)
+template <int D>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+pcg_spmv_tma_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
+                    const double* __restrict__ values, const double* __restrict__ p, double* __restrict__ ap,
+                    int64_t p_row_offset, int stages, int val_cap, int col_cap, PcgState* st, double* partials) {
+  extern __shared__ __align__(128) unsigned char s_tma[];
+  __shared__ double s_red[32];
+  if (st->done) return;
+  double dot = 0.0;
+  spmv_tma_body<D, true>(n_nodes, node_rowptr, node_colidx, values, p, ap, p + p_row_offset * D, stages, val_cap,
+                         col_cap, s_tma, dot);
+  const double total = block_sum(dot, s_red);
+  if (publish_partials(partials, 1, &total, &st->counter[0])) {
+    const double s = reduce_partials(partials, s_red);
+    if (threadIdx.x == 0) {
+      st->pap = s;
+      st->counter[0] = 0;
+    }
+  }
+}
+
+template <int D>
+static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
+                      const double* values, const double* x, double* y, int64_t off, PcgState* st, double* partials,
+                      cudaStream_t stream) {
+  const TmaLayout& L = plan.layout;
+  if (dot) {
+    FEA_TRY(check(cudaFuncSetAttribute(pcg_spmv_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)L.smem_bytes)));
+    pcg_spmv_tma_kernel<D><<<plan.grid, kTmaThreads, L.smem_bytes, stream>>>(n_nodes, rp, ci, values, x, y, off,
+                                                                           L.stages, L.val_cap, L.col_cap, st,
+                                                                           partials);
+  } else {
+    FEA_TRY(check(cudaFuncSetAttribute(spmv_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)L.smem_bytes)));
+    spmv_tma_kernel<D><<<plan.grid, kTmaThreads, L.smem_bytes, stream>>>(n_nodes, rp, ci, values, x, y, L.stages,
+                                                                       L.val_cap, L.col_cap);
+  }
+  return FEA_OK;
+}
+
+static int dispatch_tma(int d, const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
+                        const double* values, const double* x, double* y, int64_t off, PcgState* st,
+                        double* partials, cudaStream_t stream) {
+  switch (d) {
+    case 1: return launch_tma<1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 2: return launch_tma<2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 3: return launch_tma<3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    default: return FEA_ERR_INVALID;
   }
 }
 
@@ -287,7 +363,10 @@ static int launch_step_spmv(int64_t n_nodes, const int32_t* rp, const int32_t* c
 }
 
 static int step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
-                     const double* p, double* ap, int64_t off, PcgState* st, double* partials, cudaStream_t stream) {
+                     const double* p, double* ap, int64_t off, PcgState* st, double* partials, cudaStream_t stream,
+                     const TmaPlan* plan = nullptr) {
+  if (plan != nullptr && plan->ok)
+    return dispatch_tma(d, *plan, true, n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
   switch (d) {
     case 1: return launch_step_spmv<1>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
     case 2: return launch_step_spmv<2>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
@@ -301,9 +380,16 @@ static int step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* c
 using namespace fea;
 
 extern "C" int fea_spmv(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, const int32_t* node_colidx,
-                        const double* values, const double* x, double* y, void* stream_) {
+                        const double* values, int32_t max_coupled, const double* x, double* y, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!node_rowptr || !node_colidx || !values || !x || !y || n_nodes <= 0) return FEA_ERR_INVALID;
+  if (d < 1 || d > 3) return FEA_ERR_INVALID;
+  const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_nodes);
+  if (plan.ok) {
+    FEA_TRY(dispatch_tma(d, plan, false, n_nodes, node_rowptr, node_colidx, values, x, y, 0, nullptr, nullptr,
+                         stream));
+    return check_launch();
+  }
   const unsigned blocks = spmv_blocks(n_nodes);
   switch (d) {
     case 1: spmv_kernel<1><<<blocks, kSpmvThreads, 0, stream>>>(n_nodes, node_rowptr, node_colidx, values, x, y); break;
@@ -329,13 +415,15 @@ extern "C" int fea_pcg_init(int64_t n_dof, const double* b, const double* dinv, 
 }
 
 extern "C" int fea_pcg_step_spmv(int64_t n_owned_nodes, int32_t d, const int32_t* node_rowptr,
-                                 const int32_t* node_colidx, const double* values, const double* p, double* ap,
-                                 int64_t p_row_offset, void* state, void* partials, void* stream_) {
+                                 const int32_t* node_colidx, const double* values, int32_t max_coupled,
+                                 const double* p, double* ap, int64_t p_row_offset, void* state, void* partials,
+                                 void* stream_) {
   if (!node_rowptr || !node_colidx || !values || !p || !ap || !state || !partials || n_owned_nodes <= 0)
     return FEA_ERR_INVALID;
+  const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_owned_nodes);
   FEA_TRY(step_spmv(d, n_owned_nodes, node_rowptr, node_colidx, values, p, ap, p_row_offset,
                     static_cast<PcgState*>(state), static_cast<double*>(partials),
-                    static_cast<cudaStream_t>(stream_)));
+                    static_cast<cudaStream_t>(stream_), &plan));
   return check_launch();
 }
 
@@ -356,15 +444,16 @@ extern "C" int fea_pcg_step_direction(int64_t n_dof, const double* dinv, const d
 }
 
 extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, const int32_t* node_colidx,
-                             const double* values, const double* dinv, const double* b, double* x, double tol,
-                             int32_t max_iter, void* work, size_t work_bytes, double* history,
-                             fea_pcg_result* result_host, void* stream_) {
+                             const double* values, int32_t max_coupled, const double* dinv, const double* b,
+                             double* x, double tol, int32_t max_iter, void* work, size_t work_bytes,
+                             double* history, fea_pcg_result* result_host, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!node_rowptr || !node_colidx || !values || !dinv || !b || !x || !work || !result_host) return FEA_ERR_INVALID;
   if (n_nodes <= 0 || d < 1 || d > 3 || max_iter < 1) return FEA_ERR_INVALID;
   const int64_t n = n_nodes * d;
   if (work_bytes < fea_pcg_workspace(n)) return FEA_ERR_WORKSPACE;
   PcgWork w = carve_pcg(work, n);
+  const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_nodes);
 
   // two pinned snapshots of the state, polled one chunk behind the GPU
   PcgState* snap = nullptr;
@@ -400,7 +489,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     for (int it = 0; it < todo && rc == FEA_OK; ++it) {
       const bool sample = sample_ev != nullptr && it == 0 && n_samples < kMaxSamples;
       if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
-      rc = step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream);
+      rc = step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream, &plan);
       if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
       pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials);
       pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history);

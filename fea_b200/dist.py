@@ -248,8 +248,8 @@ class GpuOps:
     def step_spmv(self, p_ext, ap, state):
         pt = self.K.pattern
         _lib.check(self.lib.fea_pcg_step_spmv(self.plan.n_owned, self.d, self.rowptr_owned.data_ptr(),
-                                              pt.node_colidx.data_ptr(), self.K.values.data_ptr(), p_ext.data_ptr(),
-                                              ap.data_ptr(), self.plan.offset, state.data_ptr(),
+                                              pt.node_colidx.data_ptr(), self.K.values.data_ptr(), pt.max_coupled,
+                                              p_ext.data_ptr(), ap.data_ptr(), self.plan.offset, state.data_ptr(),
                                               self.partials.data_ptr(), self.core._stream()), "fea_pcg_step_spmv")
 
     def step_update(self, dinv, p_own, ap, x, r, state):
@@ -265,8 +265,8 @@ class GpuOps:
     def matvec_owned(self, x_ext, y_owned):
         pt = self.K.pattern
         _lib.check(self.lib.fea_spmv(self.plan.n_owned, self.d, self.rowptr_owned.data_ptr(),
-                                     pt.node_colidx.data_ptr(), self.K.values.data_ptr(), x_ext.data_ptr(),
-                                     y_owned.data_ptr(), self.core._stream()), "fea_spmv")
+                                     pt.node_colidx.data_ptr(), self.K.values.data_ptr(), pt.max_coupled,
+                                     x_ext.data_ptr(), y_owned.data_ptr(), self.core._stream()), "fea_spmv")
 
 
 def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan, tol=1e-12, max_iter=None,

@@ -161,8 +161,11 @@ int fea_jacobi_dinv(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_r
 /* y = K x on the node-block pattern (dof_per_node in {1,2,3}; 1 = ordinary CSR with
  * node_rowptr/node_colidx = rowptr/colidx). */
 int fea_spmv(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
-             const int32_t* node_colidx, const double* values, const double* x, double* y,
-             void* stream);
+             const int32_t* node_colidx, const double* values, int32_t max_coupled, const double* x,
+             double* y, void* stream);
+/* `max_coupled` (here and below): the largest number of coupled nodes of any node row, as
+ * returned by fea_csr_symbolic_count.  It sizes the shared-memory stages of the TMA bulk-copy
+ * SpMV pipeline (cp.async.bulk + mbarrier); pass 0 if unknown to use the plain-load kernel. */
 
 /* Y = K X for n_rhs right-hand sides, X and Y (n_dof, n_rhs) row-major. */
 int fea_spmm(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
@@ -187,9 +190,10 @@ typedef struct {
  *   result_host: HOST pointer (pinned preferred), filled before return (the call synchronises).
  *   history, may be NULL: device array [max_iter] receiving ||r||/||b|| per iteration. */
 int fea_pcg_solve(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
-                  const int32_t* node_colidx, const double* values, const double* dinv,
-                  const double* b, double* x, double tol, int32_t max_iter, void* work,
-                  size_t work_bytes, double* history, fea_pcg_result* result_host, void* stream);
+                  const int32_t* node_colidx, const double* values, int32_t max_coupled,
+                  const double* dinv, const double* b, double* x, double tol, int32_t max_iter,
+                  void* work, size_t work_bytes, double* history, fea_pcg_result* result_host,
+                  void* stream);
 
 /* The three kernels of one PCG iteration, exposed so that a multi-GPU driver can interleave its
  * halo exchange and all-reduces.  `state` is FEA_PCG_STATE_BYTES of device memory; viewed as
@@ -213,8 +217,9 @@ enum {
 int fea_pcg_init(int64_t n_dof, const double* b, const double* dinv, double* x, double* r, double* p,
                  double tol, int32_t max_iter, void* state, void* partials, void* stream);
 int fea_pcg_step_spmv(int64_t n_owned_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
-                      const int32_t* node_colidx, const double* values, const double* p, double* ap,
-                      int64_t p_row_offset, void* state, void* partials, void* stream);
+                      const int32_t* node_colidx, const double* values, int32_t max_coupled,
+                      const double* p, double* ap, int64_t p_row_offset, void* state, void* partials,
+                      void* stream);
 int fea_pcg_step_update(int64_t n_dof, const double* dinv, const double* p, const double* ap,
                         double* x, double* r, void* state, void* partials, void* stream);
 /* history, may be NULL: device array [max_iter], entry it-1 receives ||r||/||b|| of iteration it. */

@@ -49,7 +49,7 @@ def test_argument_validation_needs_no_gpu(lib_path):
     lib = _lib.load()
     # null pointers are rejected before any CUDA call
     assert lib.fea_ke_hex8(None, None, 1, 1.0, 0.3, None, None, None) == _lib.FEA_ERR_INVALID
-    assert lib.fea_spmv(0, 3, None, None, None, None, None, None) == _lib.FEA_ERR_INVALID
+    assert lib.fea_spmv(0, 3, None, None, None, 27, None, None, None) == _lib.FEA_ERR_INVALID
     assert lib.fea_pcg_workspace(1000) >= 3 * 8 * 1000
     assert lib.fea_csr_symbolic_workspace(1000, 100, 8) >= 4 * 1000
 

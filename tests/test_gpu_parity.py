@@ -216,10 +216,16 @@ def test_spmv_spmm_vs_scipy(mods):
     rowptr, colidx = K.pattern.csr(3)
     y1 = torch.empty(K.n_dof, dtype=torch.float64, device="cuda")
     xd = core.to_device(x, torch.float64)
-    rc = _lib.load().fea_spmv(K.n_dof, 1, rowptr.data_ptr(), colidx.data_ptr(), K.values.data_ptr(), xd.data_ptr(),
-                              y1.data_ptr(), None)
-    assert rc == 0
-    assert rel(y1.cpu().numpy(), Kref @ x) < 1e-13
+    for maxc in (0, 3 * K.pattern.max_coupled):  # 0 = generic kernel, else the bulk-copy pipeline
+        rc = _lib.load().fea_spmv(K.n_dof, 1, rowptr.data_ptr(), colidx.data_ptr(), K.values.data_ptr(), maxc,
+                                  xd.data_ptr(), y1.data_ptr(), None)
+        assert rc == 0
+        assert rel(y1.cpu().numpy(), Kref @ x) < 1e-13
+    # D = 3, generic kernel (max_coupled unknown) against the pipeline kernel
+    pt = K.pattern
+    rc = _lib.load().fea_spmv(pt.n_nodes, 3, pt.node_rowptr.data_ptr(), pt.node_colidx.data_ptr(),
+                              K.values.data_ptr(), 0, xd.data_ptr(), y1.data_ptr(), None)
+    assert rc == 0 and rel(y1.cpu().numpy(), Kref @ x) < 1e-13
     # rigid translations are in the null space of the unconstrained K (row sums vanish)
     t = np.tile([1.0, 0.0, 0.0], nodes.shape[0])
     assert np.abs(K.matvec(core.to_device(t, torch.float64)).cpu().numpy()).max() < 1e-12 * np.abs(Kref.data).max()
