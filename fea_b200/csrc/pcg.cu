@@ -19,6 +19,8 @@
 // stalling the GPU.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "spmv_tma.cuh"
 
@@ -28,7 +30,8 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
   static int sm_count = 0, smem_optin = 0;
   TmaPlan plan;
   plan.ok = false;
-  plan.grid = 0;
+  plan.max_grid = 0;
+  plan.groups = 0;
   plan.layout = TmaLayout{0, 0, 0, 0};
   if (max_coupled < 1 || d < 1 || d > 3) return plan;
   if ((reinterpret_cast<uintptr_t>(values) & 15u) || (reinterpret_cast<uintptr_t>(node_colidx) & 15u)) return plan;
@@ -39,10 +42,32 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
     cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   }
   if (sm_count <= 0 || smem_optin <= 0) return plan;
-  plan.layout = tma_layout(d, max_coupled, (size_t)smem_optin - 1024);  // static smem of the reducing kernels
-  if (plan.layout.stages < 2) return plan;
+  if (n_nodes >= (int64_t)INT32_MAX / 4) return plan;
+  // Shape of the pipeline: consumer groups per CTA, ring stages per CTA, CTAs (rings) per SM.
+  static int cfg_groups = 0, cfg_stages = 0, cfg_ctas = 0;
+  if (cfg_groups == 0) {
+    cfg_groups = 2, cfg_stages = 2, cfg_ctas = 3;  // best of the sweep on B200: profiles/tma_sweep_r01.log
+    if (const char* env = std::getenv("FEA_TMA_CFG")) {
+      int g = 0, s = 0, c = 0;
+      if (std::sscanf(env, "%d,%d,%d", &g, &s, &c) == 3 && g >= 1 && g <= kTmaMaxGroups && s >= 1 &&
+          s <= kTmaMaxStages && c >= 1 && c <= 8)
+        cfg_groups = g, cfg_stages = s, cfg_ctas = c;
+    }
+  }
+  // shared memory per SM is split between the CTAs; keep ~1 KB per CTA for static smem + reserve
+  const size_t per_cta = ((size_t)smem_optin + 1024) / cfg_ctas - 2048;
+  // The ring length is a multiple of the group count (a stage is always consumed by the same
+  // group); drop groups until one ring fits.
+  int groups = cfg_groups;
+  plan.layout = tma_layout(d, groups, max_coupled, cfg_stages, per_cta);
+  while (plan.layout.stages < 1 && groups > 1) {
+    --groups;
+    plan.layout = tma_layout(d, groups, max_coupled, cfg_stages, per_cta);
+  }
+  if (plan.layout.stages < 1) return plan;  // tile wider than shared memory
   const int64_t tiles = ceil_div(n_nodes, kTileNodes);
-  plan.grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, sm_count));
+  plan.max_grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * cfg_ctas));
+  plan.groups = groups;
   plan.ok = true;
   return plan;
 }
@@ -145,17 +170,18 @@ pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const 
 }
 
 // step 1, bulk-copy pipeline variant (spmv_tma.cuh)
-template <int D>
-__global__ void __launch_bounds__(kTmaThreads, 1)
-pcg_spmv_tma_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
+template <int D, int G>
+__global__ void __launch_bounds__(tma_threads(D, G))
+pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                     const double* __restrict__ values, const double* __restrict__ p, double* __restrict__ ap,
-                    int64_t p_row_offset, int stages, int val_cap, int col_cap, PcgState* st, double* partials) {
+                    const double* __restrict__ p_own, int stages, int val_cap, int col_cap, PcgState* st,
+                    double* partials) {
   extern __shared__ __align__(128) unsigned char s_tma[];
   __shared__ double s_red[32];
   if (st->done) return;
   double dot = 0.0;
-  spmv_tma_body<D, true>(n_nodes, node_rowptr, node_colidx, values, p, ap, p + p_row_offset * D, stages, val_cap,
-                         col_cap, s_tma, dot);
+  spmv_tma_body<D, G, true>(n_nodes, node_rowptr, node_colidx, values, p, ap, p_own, stages, val_cap, col_cap, s_tma,
+                            dot);
   const double total = block_sum(dot, s_red);
   if (publish_partials(partials, 1, &total, &st->counter[0])) {
     const double s = reduce_partials(partials, s_red);
@@ -166,33 +192,70 @@ pcg_spmv_tma_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, co
   }
 }
 
-template <int D>
+template <int D, int G>
 static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
                       const double* values, const double* x, double* y, int64_t off, PcgState* st, double* partials,
                       cudaStream_t stream) {
   const TmaLayout& L = plan.layout;
+  // Persistent kernel: never launch more CTAs than can be resident at once (a partial second
+  // wave would idle most of the chip), whatever registers / shared memory allow for this variant.
+  auto resident_grid = [&](auto kernel) -> int {
+    int per_sm = 0, sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tma_threads(D, G), L.smem_bytes) !=
+            cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    return std::min(plan.max_grid, per_sm * sms);
+  };
+  const long long key = ((long long)plan.max_grid << 32) | (long long)L.smem_bytes;
+  const int n = (int)n_nodes;
   if (dot) {
-    FEA_TRY(check(cudaFuncSetAttribute(pcg_spmv_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)L.smem_bytes)));
-    pcg_spmv_tma_kernel<D><<<plan.grid, kTmaThreads, L.smem_bytes, stream>>>(n_nodes, rp, ci, values, x, y, off,
-                                                                           L.stages, L.val_cap, L.col_cap, st,
-                                                                           partials);
+    static int grid_cache = 0;
+    static long long grid_key = -1;
+    if (grid_key != key) {
+      FEA_TRY(check(cudaFuncSetAttribute(pcg_spmv_tma_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)L.smem_bytes)));
+      grid_cache = resident_grid(pcg_spmv_tma_kernel<D, G>);
+      grid_key = key;
+    }
+    pcg_spmv_tma_kernel<D, G><<<grid_cache, tma_threads(D, G), L.smem_bytes, stream>>>(
+        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials);
   } else {
-    FEA_TRY(check(cudaFuncSetAttribute(spmv_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)L.smem_bytes)));
-    spmv_tma_kernel<D><<<plan.grid, kTmaThreads, L.smem_bytes, stream>>>(n_nodes, rp, ci, values, x, y, L.stages,
-                                                                       L.val_cap, L.col_cap);
+    static int grid_cache = 0;
+    static long long grid_key = -1;
+    if (grid_key != key) {
+      FEA_TRY(check(cudaFuncSetAttribute(spmv_tma_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)L.smem_bytes)));
+      grid_cache = resident_grid(spmv_tma_kernel<D, G>);
+      grid_key = key;
+    }
+    spmv_tma_kernel<D, G><<<grid_cache, tma_threads(D, G), L.smem_bytes, stream>>>(n, rp, ci, values, x, y, L.stages,
+                                                                              L.val_cap, L.col_cap);
   }
   return FEA_OK;
+}
+
+template <int D>
+static int launch_tma_g(const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
+                        const double* values, const double* x, double* y, int64_t off, PcgState* st,
+                        double* partials, cudaStream_t stream) {
+  switch (plan.groups) {
+    case 1: return launch_tma<D, 1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 2: return launch_tma<D, 2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 3: return launch_tma<D, 3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 4: return launch_tma<D, 4>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    default: return FEA_ERR_INVALID;
+  }
 }
 
 static int dispatch_tma(int d, const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
                         const double* values, const double* x, double* y, int64_t off, PcgState* st,
                         double* partials, cudaStream_t stream) {
   switch (d) {
-    case 1: return launch_tma<1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
-    case 2: return launch_tma<2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
-    case 3: return launch_tma<3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 1: return launch_tma_g<1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 2: return launch_tma_g<2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 3: return launch_tma_g<3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
     default: return FEA_ERR_INVALID;
   }
 }
@@ -216,7 +279,32 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
   const double alpha = rz / pap;
   double s_rz = 0.0, s_rr = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 4 independent elements per trip, every load issued before the first use (HBM-bound, 7 streams)
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    double di[4], pi[4], ai[4], ri[4], xi[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = i + u * stride;
+      di[u] = dinv[j];
+      pi[u] = p[j];
+      ai[u] = __ldcs(ap + j);  // ap and x are not needed again before they are rewritten
+      ri[u] = r[j];
+      xi[u] = __ldcs(x + j);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = i + u * stride;
+      const double rn = fma(-alpha, ai[u], ri[u]);
+      __stcs(x + j, fma(alpha, pi[u], xi[u]));
+      r[j] = rn;
+      if (di[u] != 0.0) {
+        s_rz = fma(rn * di[u], rn, s_rz);
+        s_rr = fma(rn, rn, s_rr);
+      }
+    }
+  }
+  for (; i < n; i += stride) {
     const double di = dinv[i];
     const double pi = p[i];
     const double ri = fma(-alpha, ap[i], r[i]);
@@ -253,8 +341,20 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
   if (!converged) {
     const double beta = rz_new / rz;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-      p[i] = fma(beta, p[i], dinv[i] * r[i]);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+      double di[4], ri[4], pi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t j = i + u * stride;
+        di[u] = dinv[j];
+        ri[u] = r[j];
+        pi[u] = p[j];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[i + u * stride] = fma(beta, pi[u], di[u] * ri[u]);
+    }
+    for (; i < n; i += stride) p[i] = fma(beta, p[i], dinv[i] * r[i]);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -321,6 +421,7 @@ pcg_init_kernel(int64_t n, const double* __restrict__ b, const double* __restric
 }
 
 inline unsigned vec_blocks(int64_t n) {
+  // 8 resident CTAs of 256 threads per SM, one full wave (<= kMaxPartials blocks)
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 4), 148LL * 8));
 }
 inline unsigned spmv_blocks(int64_t n_nodes) {

@@ -3,38 +3,52 @@
 // Why: the matrix stream (values + node-level column indices) of a run of consecutive nodes is
 // ONE contiguous byte range of each array, so a single elected thread can stream it into shared
 // memory with 1-D bulk copies (SASS: UBLKCP) through a ring of stages, completely decoupled
-// from the warps that consume it.  That keeps kStages x ~33 KB of HBM reads in flight per SM
-// regardless of register pressure or instruction scheduling -- the plain-load kernel (spmv.cuh)
-// only reaches ~2 KB per warp and ptxas serialises its loads when registers get tight.
+// from the warps that consume it.  That keeps whole tiles (~33 KB on a hex8 mesh) of HBM reads
+// in flight per SM regardless of register pressure or instruction scheduling -- the plain-load
+// kernel (spmv.cuh) only reaches ~2 KB per warp and ptxas serialises its loads when registers
+// get tight (1.8 ms vs 0.8 ms per SpMV at 400x80x80).
 //
-// Once a tile sits in shared memory, random access is cheap, so the consumers work
-// THREAD-PER-ROW ("CSR-stream"): lane <-> one DOF row of the tile.  Consecutive lanes read
-// shared memory at a stride of one row (81 doubles on a hex8 mesh: odd, hence conflict-free),
-// the D lanes of a node gather the same x entries (broadcast) and neighbouring nodes gather
-// neighbouring entries (few sectors per request), there is no cross-lane reduction at all, and
-// y is written with unit stride.
+// Once a tile sits in shared memory, random access is cheap, so the consumers do not work
+// warp-per-row.  A tile of 16 nodes has 16*D rows; every row is split by column component b
+// into D partial products, and one lane owns one (row, b) pair:
+//     partial(row, b) = sum_k  V[row][D*k + b] * x[D*col_k + b]
+//   * lanes are ordered b-major, so the 32 lanes of a warp read shared memory at a stride of one
+//     row (81 doubles on a hex8 mesh: odd => conflict-free 64-bit accesses);
+//   * all gathers of a lane (27 on a hex8 mesh) are issued back to back: a tile costs about ONE
+//     L2 round trip -- under a saturated memory system that latency is what bounds a consumer,
+//     so several groups of 5 warps keep > 10k gathers in flight per SM;
+//   * neighbouring rows gather neighbouring x entries (few sectors per request, L1 hits);
+//   * the D partials of a row meet in shared memory (double-buffered, one named barrier per
+//     tile and group); y is written with unit stride.  No warp shuffles, no atomics.
 //
-//   producer (1 thread)      for tile q = 0, 1, ... of this CTA: wait empty[q % S]; expect_tx;
-//                            bulk-copy values[D*D*rp[n0] .. D*D*rp[n1]) and
-//                            node_colidx[rp[n0] .. rp[n1]) into stage q % S
-//   consumer groups (G x 2 warps)  group g takes tiles q = g, g+G, ...: wait full[q % S];
-//                            row-per-lane products with 9 node columns (27 gathers) in flight;
-//                            arrive on empty[q % S]
-// Persistent grid (one CTA per SM); tile = blockIdx + gridDim * q, so the chip sweeps one
-// contiguous window of the matrix and of x at a time.
+//   producer warp         tile q = 0, 1, ... of this CTA: wait empty[q % S]; expect_tx;
+//                         bulk-copy values[D*D*rp[n0] .. D*D*rp[n1]) and node_colidx[rp[n0] .. rp[n1])
+//   consumer group g      tiles q = g, g+G, ...: wait full[q % S]; partials; arrive empty[q % S]
+// S is a multiple of G, so a stage is always consumed by the same group (mbarrier phase
+// discipline).  Several CTAs (= independent rings) share an SM: tools/membench.cu shows one deep
+// ring per SM streams 6.2 TB/s, 3 independent rings 6.9 TB/s.  Persistent grid;
+// tile = blockIdx + gridDim * q, so the chip sweeps one contiguous window of the matrix and of
+// x at a time.
 #pragma once
 #include "spmv.cuh"
 
 namespace fea {
 
-constexpr int kTileNodes = 16;
-constexpr int kTmaGroups = 4;
-constexpr int kTmaGroupWarps = 2;  // 64 lanes >= D * kTileNodes rows for D <= 3 (static_assert below)
-constexpr int kTmaConsumerWarps = kTmaGroups * kTmaGroupWarps;
-constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;  // + 1 producer warp
-constexpr int kTmaMaxStages = 5;       // ~164 KB on a hex8 mesh: leaves ~90 KB of the SM array to L1 for the x gathers
-constexpr int kTmaBarrierBytes = 128;  // full[kTmaMaxStages], empty[kTmaMaxStages], padded
-constexpr int kTmaUnroll = 9;          // node columns per round: D * 9 gathers in flight per lane
+#ifndef FEA_TILE_NODES
+#define FEA_TILE_NODES 16
+#endif
+constexpr int kTileNodes = FEA_TILE_NODES;
+constexpr int kTmaMaxGroups = 4;
+constexpr int kTmaMaxStages = 8;
+constexpr int kTmaBarrierBytes = 128;  // full[kTmaMaxStages], empty[kTmaMaxStages]
+constexpr int kTmaUnroll = 27;         // gathers in flight per lane and round
+
+__host__ __device__ constexpr int tma_items(int d) { return d * d * kTileNodes; }  // (row, b) pairs per tile
+__host__ __device__ constexpr int tma_group_warps(int d) { return (tma_items(d) + 31) / 32; }
+__host__ __device__ constexpr int tma_threads(int d, int groups) { return (groups * tma_group_warps(d) + 1) * 32; }
+__host__ __device__ constexpr size_t tma_fixed_bytes(int d, int groups) {
+  return kTmaBarrierBytes + sizeof(double) * 2 * groups * tma_items(d);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -68,6 +82,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void group_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 struct TmaLayout {
   int stages;
@@ -78,124 +95,120 @@ struct TmaLayout {
 
 // Stage capacity for the worst tile: kTileNodes nodes of `maxc` coupled nodes each, plus the
 // slack that rounding the byte range out to 16 B needs.
-inline TmaLayout tma_layout(int d, int maxc, size_t smem_limit) {
+inline TmaLayout tma_layout(int d, int groups, int maxc, int max_stages, size_t smem_limit) {
   TmaLayout L;
   L.val_cap = kTileNodes * d * d * maxc + 2;
   L.val_cap += L.val_cap & 1;
   L.col_cap = (kTileNodes * maxc + 8 + 3) & ~3;
   const size_t per_stage = sizeof(double) * L.val_cap + sizeof(int32_t) * L.col_cap;
-  const size_t fixed = kTmaBarrierBytes;
-  int s = (int)((smem_limit - fixed) / per_stage);
-  L.stages = s > kTmaMaxStages ? kTmaMaxStages : s;
-  L.smem_bytes = fixed + (size_t)(L.stages > 0 ? L.stages : 0) * per_stage;
+  const size_t fixed = tma_fixed_bytes(d, groups);
+  int s = smem_limit > fixed ? (int)((smem_limit - fixed) / per_stage) : 0;
+  if (s > max_stages) s = max_stages;
+  if (s > kTmaMaxStages) s = kTmaMaxStages;
+  s -= s % groups;  // a stage is always consumed by the same group
+  L.stages = s;
+  L.smem_bytes = fixed + (size_t)s * per_stage;
   return L;
 }
 
 // Byte ranges of one tile, rounded out to 16 B; `direct` when the rounding would run past the end
 // of the arrays (only the last tile(s) of the matrix): those are read with plain loads instead.
 struct TileRange {
-  int64_t v_lo, v_hi, c_lo, c_hi;
+  int v_lo, v_hi, c_lo, c_hi;  // element indices (< 2^31: the library requires int32 nnz)
   bool direct;
 };
 template <int D>
-__device__ __forceinline__ TileRange tile_range(int64_t r0, int64_t r1, int64_t total_vals, int64_t total_cols) {
+__device__ __forceinline__ TileRange tile_range(int r0, int r1, int total_cols) {
   TileRange t;
-  t.v_lo = (D * D * r0) & ~1LL;
-  t.v_hi = (D * D * r1 + 1) & ~1LL;
-  t.c_lo = r0 & ~3LL;
-  t.c_hi = (r1 + 3) & ~3LL;
-  t.direct = t.v_hi > total_vals || t.c_hi > total_cols;
+  t.v_lo = (D * D * r0) & ~1;
+  t.v_hi = (D * D * r1 + 1) & ~1;
+  t.c_lo = r0 & ~3;
+  t.c_hi = (r1 + 3) & ~3;
+  t.direct = t.v_hi > D * D * total_cols || t.c_hi > total_cols;
   return t;
 }
 
-// One DOF row against x: `vrow` points at the row's values, `cols` at the node's column list
-// (shared or global memory).  kTmaUnroll node columns per round, all gathers issued first.
+// Component b of one DOF row against x: sum_k vrow[D*k + b] * x[D*cols[k] + b].
+// `vrow` / `cols` may point to shared or global memory.  Every gather of a round is issued
+// before the first FMA.
 template <int D>
-__device__ __forceinline__ double row_dot(const double* vrow, const int32_t* cols, int cnt,
-                                          const double* __restrict__ x) {
-  double acc[D];
-#pragma unroll
-  for (int b = 0; b < D; ++b) acc[b] = 0.0;
+__device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t* cols, int cnt, int b,
+                                               const double* __restrict__ x) {
+  double acc = 0.0;
+  const double* xb = x + b;
+  const double* vb = vrow + b;
   for (int k0 = 0; k0 < cnt; k0 += kTmaUnroll) {
-    double xv[kTmaUnroll][D];
+    double xv[kTmaUnroll];
 #pragma unroll
     for (int u = 0; u < kTmaUnroll; ++u) {
       const int k = k0 + u;
-      if (k < cnt) {
-        const int64_t col = (int64_t)D * cols[k];
-#pragma unroll
-        for (int b = 0; b < D; ++b) xv[u][b] = __ldg(x + col + b);
-      }
+      xv[u] = k < cnt ? __ldg(xb + (int64_t)D * cols[k]) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < kTmaUnroll; ++u) {
       const int k = k0 + u;
-      if (k < cnt) {
-#pragma unroll
-        for (int b = 0; b < D; ++b) acc[b] = fma(vrow[D * k + b], xv[u][b], acc[b]);
-      }
+      if (k < cnt) acc = fma(vb[D * k], xv[u], acc);
     }
   }
-  double s = acc[0];
-#pragma unroll
-  for (int b = 1; b < D; ++b) s += acc[b];
-  return s;
+  return acc;
 }
 
 // DOT: also accumulate sum_owned x_own[row] * y[row] (the PCG p.Ap); the caller reduces `dot`.
-template <int D, bool DOT>
-__device__ __forceinline__ void spmv_tma_body(int64_t n_nodes, const int32_t* __restrict__ node_rowptr,
+template <int D, int G, bool DOT>
+__device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __restrict__ node_rowptr,
                                               const int32_t* __restrict__ node_colidx,
                                               const double* __restrict__ values, const double* __restrict__ x,
                                               double* __restrict__ y, const double* __restrict__ x_own, int stages,
                                               int val_cap, int col_cap, unsigned char* smem, double& dot) {
-  static_assert(D * kTileNodes <= kTmaGroupWarps * 32, "one lane per row of a tile");
   constexpr int DD = D * D;
+  constexpr int ROWS = D * kTileNodes;  // rows per tile
+  constexpr int ITEMS = tma_items(D);   // (row, b) pairs per tile
+  constexpr int GW = tma_group_warps(D);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kTmaMaxStages;
-  unsigned char* stage0 = smem + kTmaBarrierBytes;
-  const size_t stage_bytes = sizeof(double) * val_cap + sizeof(int32_t) * col_cap;
+  double* parts = reinterpret_cast<double*>(smem + kTmaBarrierBytes);  // [2][G][ITEMS]
+  unsigned char* stage0 = smem + tma_fixed_bytes(D, G);
+  const int stage_bytes = (int)(sizeof(double) * val_cap + sizeof(int32_t) * col_cap);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kTmaGroupWarps);
+      mbar_init(&empty[s], GW);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  const int64_t n_tiles = (n_nodes + kTileNodes - 1) / kTileNodes;
-  const int64_t total_cols = node_rowptr[n_nodes];
-  const int64_t total_vals = (int64_t)DD * total_cols;
+  const int n_tiles = (n_nodes + kTileNodes - 1) / kTileNodes;
+  const int total_cols = node_rowptr[n_nodes];
+  const int stride = (int)gridDim.x;
 
-  if (warp == kTmaConsumerWarps) {
+  if (warp == G * GW) {
     // ------------------------------------------------------------------ producer
     // The whole warp fetches the row pointers of the next 32 tiles at once (one memory latency
-    // per 32 tiles instead of one per tile -- a single thread chasing rp[] tile by tile caps the
-    // CTA at one tile per DRAM round trip); lane 0 then issues the copies.
-    auto fetch = [&](int64_t q, int& a0, int& a1) {
-      const int64_t t = blockIdx.x + (int64_t)gridDim.x * q;
+    // per 32 tiles instead of one per tile); lane 0 then issues the copies.
+    auto fetch = [&](int q, int& a0, int& a1) {
+      const int64_t t = blockIdx.x + (int64_t)stride * q;
       a0 = a1 = 0;
       if (t < n_tiles) {
-        const int64_t n0 = t * kTileNodes;
+        const int n0 = (int)t * kTileNodes;
         a0 = node_rowptr[n0];
         a1 = node_rowptr[n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes];
       }
     };
     int nxt_r0, nxt_r1;
     fetch(lane, nxt_r0, nxt_r1);
-    for (int64_t q0 = 0; blockIdx.x + (int64_t)gridDim.x * q0 < n_tiles; q0 += 32) {
+    for (int q0 = 0; blockIdx.x + (int64_t)stride * q0 < n_tiles; q0 += 32) {
       const int my_r0 = nxt_r0, my_r1 = nxt_r1;
       fetch(q0 + 32 + lane, nxt_r0, nxt_r1);  // the batch after this one, in flight while this one is issued
       for (int j = 0; j < 32; ++j) {
         const int r0 = __shfl_sync(kFull, my_r0, j), r1 = __shfl_sync(kFull, my_r1, j);
-        const int64_t q = q0 + j;
-        if (blockIdx.x + (int64_t)gridDim.x * q >= n_tiles) break;  // warp-uniform
-        const TileRange t = tile_range<D>(r0, r1, total_vals, total_cols);
+        const int q = q0 + j;
+        if (blockIdx.x + (int64_t)stride * q >= n_tiles) break;  // warp-uniform
+        const TileRange t = tile_range<D>(r0, r1, total_cols);
         if (lane == 0 && !t.direct) {
-          const int s = (int)(q % stages);
+          const int s = q % stages;
           const uint32_t ph = (uint32_t)(q / stages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           unsigned char* buf = stage0 + (size_t)s * stage_bytes;
@@ -209,35 +222,37 @@ __device__ __forceinline__ void spmv_tma_body(int64_t n_nodes, const int32_t* __
     }
   } else {
     // ------------------------------------------------------------------ consumers
-    const int group = warp / kTmaGroupWarps;
-    const int row = (warp % kTmaGroupWarps) * 32 + lane;  // row of the tile owned by this lane
+    const int group = warp / GW;
+    const int item = (warp - group * GW) * 32 + lane;  // b-major: item = b * ROWS + row
+    const bool has_item = item < ITEMS;
+    const int b = has_item ? item / ROWS : 0;
+    const int row = has_item ? item - b * ROWS : 0;
     const int node_in_tile = row / D, a = row - node_in_tile * D;
-    int64_t tile = blockIdx.x + (int64_t)gridDim.x * group;
+    double* parts_g = parts + group * ITEMS;
+    int64_t tile64 = blockIdx.x + (int64_t)stride * group;
     // row pointers of this lane's node for the first tile; later tiles are prefetched one ahead
-    int64_t r0 = 0, r1 = 0;
-    int lo = 0, hi = 0;
-    if (tile < n_tiles) {
-      const int64_t n0 = tile * kTileNodes;
-      const int64_t n1 = n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes;
-      const int64_t node = n0 + node_in_tile;
+    int r0 = 0, r1 = 0, lo = 0, hi = 0;
+    if (tile64 < n_tiles) {
+      const int n0 = (int)tile64 * kTileNodes;
+      const int n1 = n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes;
       r0 = node_rowptr[n0];
       r1 = node_rowptr[n1];
-      if (node < n1) {
-        lo = node_rowptr[node];
-        hi = node_rowptr[node + 1];
+      if (n0 + node_in_tile < n1) {
+        lo = node_rowptr[n0 + node_in_tile];
+        hi = node_rowptr[n0 + node_in_tile + 1];
       }
     }
-    for (int q = group; tile < n_tiles; q += kTmaGroups) {
-      const int64_t n0 = tile * kTileNodes;
-      const int64_t n1 = n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes;
-      const int64_t node = n0 + node_in_tile;
-      const bool active = node < n1;
-      const int64_t next = tile + (int64_t)gridDim.x * kTmaGroups;
-      int64_t nr0 = 0, nr1 = 0;
-      int nlo = 0, nhi = 0;
-      if (next < n_tiles) {
-        const int64_t m0 = next * kTileNodes;
-        const int64_t m1 = m0 + kTileNodes < n_nodes ? m0 + kTileNodes : n_nodes;
+    int buf_sel = 0;
+    for (int q = group; tile64 < n_tiles; q += G) {
+      const int n0 = (int)tile64 * kTileNodes;
+      const int n1 = n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes;
+      const int node = n0 + node_in_tile;
+      const bool active = has_item && node < n1;
+      tile64 += (int64_t)stride * G;
+      int nr0 = 0, nr1 = 0, nlo = 0, nhi = 0;
+      if (tile64 < n_tiles) {
+        const int m0 = (int)tile64 * kTileNodes;
+        const int m1 = m0 + kTileNodes < n_nodes ? m0 + kTileNodes : n_nodes;
         nr0 = node_rowptr[m0];
         nr1 = node_rowptr[m1];
         if (m0 + node_in_tile < m1) {
@@ -245,29 +260,36 @@ __device__ __forceinline__ void spmv_tma_body(int64_t n_nodes, const int32_t* __
           nhi = node_rowptr[m0 + node_in_tile + 1];
         }
       }
-      const TileRange t = tile_range<D>(r0, r1, total_vals, total_cols);
+      const TileRange t = tile_range<D>(r0, r1, total_cols);
       const int cnt = hi - lo;
-      double out = 0.0;
+      double part = 0.0;
       if (t.direct) {
-        if (active) out = row_dot<D>(values + (int64_t)DD * lo + (int64_t)a * D * cnt, node_colidx + lo, cnt, x);
+        if (active)
+          part = row_part_dot<D>(values + (int64_t)DD * lo + a * D * cnt, node_colidx + lo, cnt, b, x);
       } else {
         const int s = q % stages;
         const uint32_t ph = (uint32_t)(q / stages) & 1u;
         mbar_wait(&full[s], ph);
         if (active) {
           const unsigned char* buf = stage0 + (size_t)s * stage_bytes;
-          const double* vs = reinterpret_cast<const double*>(buf) + ((int64_t)DD * lo - t.v_lo);
+          const double* vs = reinterpret_cast<const double*>(buf) + (DD * lo - t.v_lo);
           const int32_t* cs = reinterpret_cast<const int32_t*>(buf + sizeof(double) * val_cap) + (lo - t.c_lo);
-          out = row_dot<D>(vs + a * D * cnt, cs, cnt, x);
+          part = row_part_dot<D>(vs + a * D * cnt, cs, cnt, b, x);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
       }
-      if (active) {
-        y[node * D + a] = out;
-        if (DOT) dot = fma(out, x_own[node * D + a], dot);
+      double* my_parts = parts_g + buf_sel * (G * ITEMS);
+      if (has_item) my_parts[item] = part;
+      group_barrier(1 + group, GW * 32);
+      if (active && b == 0) {  // items 0 .. ROWS-1 finish their row
+        double out = part;
+#pragma unroll
+        for (int bb = 1; bb < D; ++bb) out += my_parts[bb * ROWS + row];
+        y[(int64_t)node * D + a] = out;
+        if (DOT) dot = fma(out, x_own[(int64_t)node * D + a], dot);
       }
-      tile = next;
+      buf_sel ^= 1;
       r0 = nr0;
       r1 = nr1;
       lo = nlo;
@@ -276,23 +298,24 @@ __device__ __forceinline__ void spmv_tma_body(int64_t n_nodes, const int32_t* __
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(kTmaThreads, 1)
-spmv_tma_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
+template <int D, int G>
+__global__ void __launch_bounds__(tma_threads(D, G))
+spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                 const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y, int stages,
                 int val_cap, int col_cap) {
   extern __shared__ __align__(128) unsigned char s_tma[];
   double dot = 0.0;
-  spmv_tma_body<D, false>(n_nodes, node_rowptr, node_colidx, values, x, y, nullptr, stages, val_cap, col_cap, s_tma,
-                          dot);
+  spmv_tma_body<D, G, false>(n_nodes, node_rowptr, node_colidx, values, x, y, nullptr, stages, val_cap, col_cap,
+                             s_tma, dot);
 }
 
-// Can the bulk-copy path be used for this matrix on this device?  (16 B aligned arrays, at
-// least two stages of shared memory for the widest tile.)
+// Can the bulk-copy path be used for this matrix on this device?  (16 B aligned arrays, enough
+// shared memory for the widest tile, int32 node count.)
 struct TmaPlan {
   bool ok;
   TmaLayout layout;
-  int grid;
+  int max_grid;  // SMs x target CTAs per SM, capped by the number of tiles
+  int groups;    // consumer groups per CTA: 1 .. 4
 };
 
 TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_colidx, int64_t n_nodes);

@@ -160,6 +160,13 @@ int main(int argc, char** argv) {
     float ms = time_ms([&] { tma_stream<<<sms, 64, smem>>>(src, bytes, c[0], c[1], c[2], out); }, 10);
     printf(", \"tma_%dk_x%d_touch%d_gbs\": %.0f", c[0] / 1024, c[1], c[2], bytes / ms / 1e6);
   }
+  // several CTAs (= several independent rings / producer threads) per SM
+  const int multi[][3] = {{32768, 3, 2}, {32768, 2, 3}, {16384, 3, 4}, {32768, 1, 6}, {2048, 8, 8}, {34816, 3, 2}};
+  for (auto& c : multi) {
+    const size_t smem = 256 + (size_t)c[0] * c[1];
+    float ms = time_ms([&] { tma_stream<<<sms * c[2], 64, smem>>>(src, bytes / c[0] * c[0], c[0], c[1], 0, out); }, 10);
+    printf(", \"tma_%dB_x%d_%dcta_gbs\": %.0f", c[0], c[1], c[2], bytes / ms / 1e6);
+  }
   CK(cudaFuncSetAttribute(tma_stream_mp, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   const int mp[][3] = {{16384, 8, 1}, {16384, 8, 2}, {16384, 8, 4}, {8192, 16, 1}, {8192, 16, 4}, {32768, 4, 2}, {32768, 6, 4}, {2048, 16, 1}, {2048, 16, 8}};
   for (auto& c : mp) {
