@@ -505,10 +505,26 @@ extern "C" size_t fea_pcg_workspace(int64_t n_dof) {
   return FEA_PCG_STATE_BYTES + sizeof(double) * 2 * kMaxPartials + 3 * align_up(sizeof(double) * (size_t)n_dof, 256);
 }
 
+// The SpMV kernel wants (almost) the whole SM array as shared memory; the vector kernels of the
+// same iteration would default to a large L1.  Alternating carve-outs makes every launch wait for
+// an SM reconfiguration (~25 us per launch measured at 100x20x20, where a whole iteration is
+// otherwise ~35 us), so the vector kernels ask for the SpMV's carve-out: they stream and do not
+// need L1.
+static void match_carveout() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncSetAttribute(pcg_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(pcg_direction_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(pcg_init_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 extern "C" int fea_pcg_init(int64_t n_dof, const double* b, const double* dinv, double* x, double* r, double* p,
                             double tol, int32_t max_iter, void* state, void* partials, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!b || !dinv || !x || !r || !p || !state || !partials || n_dof <= 0) return FEA_ERR_INVALID;
+  match_carveout();
   FEA_TRY(check(cudaMemsetAsync(state, 0, FEA_PCG_STATE_BYTES, stream)));
   pcg_init_kernel<<<vec_blocks(n_dof), 256, 0, stream>>>(n_dof, b, dinv, x, r, p, tol, max_iter,
                                                         static_cast<PcgState*>(state), static_cast<double*>(partials));
@@ -571,6 +587,22 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     return rc;
   }
 
+  // The solve runs on a private stream ordered after `stream` (and `stream` is ordered after it
+  // at the end): the caller's stream may be the legacy default stream, which cannot be captured.
+  cudaStream_t caller = stream;
+  cudaStream_t own = nullptr;
+  cudaEvent_t ev_order = nullptr;
+  if (std::getenv("FEA_PCG_NO_GRAPH") == nullptr &&
+      cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) == cudaSuccess &&
+      cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming) == cudaSuccess &&
+      cudaEventRecord(ev_order, caller) == cudaSuccess && cudaStreamWaitEvent(own, ev_order, 0) == cudaSuccess) {
+    stream = own;
+  } else if (own != nullptr) {
+    cudaStreamDestroy(own);
+    own = nullptr;
+    cudaGetLastError();
+  }
+
   rc = fea_pcg_init(n, b, dinv, x, w.r, w.p, tol, max_iter, w.state, w.partials, stream);
   const unsigned vb = vec_blocks(n);
   const int chunk = 32;
@@ -585,15 +617,43 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     sample_ev = new cudaEvent_t[2 * kMaxSamples];
     for (int i = 0; i < 2 * kMaxSamples; ++i) cudaEventCreate(&sample_ev[i]);
   }
+  int sample_iter[kMaxSamples];
+  auto enqueue_iteration = [&](bool sample) -> int {
+    if (sample) sample_iter[n_samples] = enqueued;  // 0-based index of the iteration being timed
+    if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
+    const int r = step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream,
+                            &plan);
+    if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
+    pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials);
+    pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history);
+    return r;
+  };
+  // One iteration is launched directly (it carries the timing sample), the other chunk-1 are one
+  // CUDA-graph launch: the kernel arguments never change, and small problems (100x20x20: ~35 us
+  // of kernels per iteration) are otherwise bound by the host's launch rate.
+  cudaGraphExec_t graph_exec = nullptr;
+  if (own != nullptr && rc == FEA_OK && max_iter >= chunk) {
+    enqueue_iteration(false);  // warm: every cudaFuncSetAttribute / occupancy query happens outside capture
+    rc = check_launch(3);
+    enqueued += 1;
+    cudaGraph_t graph = nullptr;
+    if (rc == FEA_OK && cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      for (int it = 0; it < chunk - 1; ++it) enqueue_iteration(false);
+      if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || graph == nullptr ||
+          cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess)
+        graph_exec = nullptr;
+      if (graph != nullptr) cudaGraphDestroy(graph);
+    }
+    cudaGetLastError();  // a failed capture falls back to plain launches
+  }
   while (rc == FEA_OK && !finished) {
     const int todo = std::min(chunk, max_iter - enqueued);
-    for (int it = 0; it < todo && rc == FEA_OK; ++it) {
-      const bool sample = sample_ev != nullptr && it == 0 && n_samples < kMaxSamples;
-      if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
-      rc = step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream, &plan);
-      if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
-      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials);
-      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history);
+    if (graph_exec != nullptr && todo == chunk) {
+      rc = enqueue_iteration(sample_ev != nullptr && n_samples < kMaxSamples);
+      if (rc == FEA_OK) rc = check(cudaGraphLaunch(graph_exec, stream));
+    } else {
+      for (int it = 0; it < todo && rc == FEA_OK; ++it)
+        rc = enqueue_iteration(sample_ev != nullptr && it == 0 && n_samples < kMaxSamples);
     }
     if (rc == FEA_OK) rc = check_launch(3 * todo);
     if (rc != FEA_OK) break;
@@ -629,7 +689,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     result_host->rel_residual = s.bnorm2 > 0.0 ? std::sqrt(s.rr / s.bnorm2) : 0.0;
     profile().pcg_iterations += s.iter;
     for (int i = 0; i < n_samples; ++i) {
-      if (i * chunk >= s.iter) break;  // launches after convergence are no-ops: not SpMV work
+      if (sample_iter[i] >= s.iter) break;  // launches after convergence are no-ops: not SpMV work
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, sample_ev[2 * i], sample_ev[2 * i + 1]) == cudaSuccess) {
         profile().spmv_ms += ms;
@@ -646,5 +706,12 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
   cudaFreeHost(snap);
+  if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
+  if (own != nullptr) {
+    // the solve has been synchronised above; order the caller's stream after it anyway
+    if (ev_order != nullptr && cudaEventRecord(ev_order, own) == cudaSuccess) cudaStreamWaitEvent(caller, ev_order, 0);
+    cudaStreamDestroy(own);
+  }
+  if (ev_order != nullptr) cudaEventDestroy(ev_order);
   return rc;
 }

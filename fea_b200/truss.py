@@ -68,9 +68,10 @@ def relax(nodes, members, loads, n_steps, member_stiffness=None):
 def member_stiffness_matrices(nodes, members, k) -> torch.Tensor:
     """(M, 6, 6) tangent stiffness k [[cc^T, -cc^T], [-cc^T, cc^T]] per member (SURVEY.md T1')."""
     lib = _lib.load()
-    nodes_d = core.to_device(np.asarray(nodes, dtype=np.float64), torch.float64)
-    members_d = core.to_device(np.asarray(members, dtype=np.int64).reshape(-1, 2), torch.int32)
-    k_d = core.to_device(np.asarray(k, dtype=np.float64), torch.float64)
+    host = lambda a, dt: a if isinstance(a, torch.Tensor) else np.asarray(a, dtype=dt)
+    nodes_d = core.to_device(host(nodes, np.float64), torch.float64)
+    members_d = core.to_device(host(members, np.int64), torch.int32).reshape(-1, 2)
+    k_d = core.to_device(host(k, np.float64), torch.float64)
     m = members_d.shape[0]
     ke = torch.empty((m, 6, 6), dtype=torch.float64, device=nodes_d.device)
     status = core._status_slot()

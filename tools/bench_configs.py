@@ -1,0 +1,130 @@
+"""Secondary BASELINE configs on one B200 (bench.py covers the headline config 4):
+
+  config 2  Euler-Bernoulli cantilever, 100k elements: Ke + assembly throughput, pattern check;
+            solve parity is only meaningful for n <= 1000 and lives in the tests
+  config 3  hex8 cantilever 100x20x20: assemble + solve, stage timings
+  config 5  jittered lattice space truss, n=93 (10.2 M members), 64 load cases: member Ke + assembly
+            elem/s, SpMM GB/s, batched multi-RHS PCG to 1e-12 on all columns
+
+    python tools/bench_configs.py [2] [3] [5] [--lattice N]
+
+Prints one JSON line per config (CUDA-event timings, inputs resident in HBM).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fea_b200 import core, cubebeam, euler_bernoulli as eb, truss  # noqa: E402
+
+E_HEX, NU_HEX = 10_000_000 * 6894.76, 0.3
+
+
+def timed(fn, reps=1):
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        out = fn()
+    c.record()
+    torch.cuda.synchronize()
+    return out, a.elapsed_time(c) / reps
+
+
+def config2(n=100_000):
+    elements, EI, Ls, cons, loads = eb.cantilever_case(n)
+    el = core.to_device(elements, torch.int32)
+    EI_d, L_d = core.to_device(EI, torch.float64), core.to_device(Ls, torch.float64)
+    fixed = core._fixed_mask(cons, 2 * (n + 1))
+    for _ in range(3):
+        pat = core.symbolic(el, n + 1)
+        K = core.assemble_beam(EI_d, L_d, el, n + 1, pattern=pat, fixed=fixed)
+    pat, ms_sym = timed(lambda: core.symbolic(el, n + 1), 5)
+    K, ms_num = timed(lambda: core.assemble_beam(EI_d, L_d, el, n + 1, pattern=pat, fixed=fixed), 20)
+    _, ms_ke = timed(lambda: eb.beam_stiffness_matrices(EI_d, L_d), 20)
+    rowptr, colidx = (t.cpu().numpy() for t in pat.csr(2))
+    # structural pattern of a chain: rows of node i couple nodes i-1, i, i+1
+    ok = K.nnz == 4 * (3 * (n + 1) - 2) and rowptr[-1] == K.nnz and np.all(np.diff(colidx.reshape(-1)[:8]) != 0)
+    print(json.dumps({"config": 2, "workload": f"Euler-Bernoulli cantilever, {n} elements", "dof": 2 * (n + 1),
+                      "nnz": K.nnz, "pattern_ok": bool(ok), "ms": {"symbolic": ms_sym, "numeric": ms_num, "ke": ms_ke},
+                      "elem_per_s": {"symbolic": n / ms_sym * 1e3, "numeric_incl_ke": n / ms_num * 1e3,
+                                     "ke_materialised": n / ms_ke * 1e3},
+                      "note": "solve not reported at this size: cond(K) ~ 5e20 (SURVEY.md H3); parity at n <= 1000 in tests"}))
+
+
+def config3(A=100, b=20):
+    nodes, elements, cons, forces = cubebeam.cantilever_case(A, b)
+    nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
+    fixed = core._fixed_mask(cons, nodes.size)
+    loads = core.to_device(forces, torch.float64).reshape(-1)
+    for _ in range(2):
+        pat = core.symbolic(el, nodes.shape[0])
+        K = core.assemble_hex8(nd, el, E_HEX, NU_HEX, pattern=pat, fixed=fixed)
+        u, info = core.pcg(K, loads)
+    pat, ms_sym = timed(lambda: core.symbolic(el, nodes.shape[0]), 5)
+    K, ms_num = timed(lambda: core.assemble_hex8(nd, el, E_HEX, NU_HEX, pattern=pat, fixed=fixed), 10)
+    (u, info), ms_solve = timed(lambda: core.pcg(K, loads), 3)
+    x = torch.randn(K.n_dof, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    _, ms_spmv = timed(lambda: K.matvec(x, out=y), 50)
+    n_free = int((cons == 0).sum())
+    total = ms_sym + ms_num + ms_solve
+    print(json.dumps({"config": 3, "workload": f"hex8 cantilever {A}x{b}x{b}", "dof": K.n_dof, "free_dof": n_free,
+                      "nnz": K.nnz, "pcg_iterations": info.iterations, "rel_residual": info.rel_residual,
+                      "ms": {"symbolic": ms_sym, "numeric": ms_num, "solve": ms_solve, "spmv": ms_spmv,
+                             "pcg_iteration": ms_solve / info.iterations},
+                      "solved_dof_per_s": n_free / total * 1e3,
+                      "assembly_elem_per_s": {"symbolic": elements.shape[0] / ms_sym * 1e3,
+                                              "numeric_incl_ke": elements.shape[0] / ms_num * 1e3},
+                      "spmv_gb_per_s_algorithmic": (12 * K.nnz + 20 * K.n_dof) / ms_spmv / 1e6,
+                      "note": "matrix (85 MB) is L2-resident at this size: SpMV is an L2 number, not HBM"}))
+
+
+def config5(n=93, n_rhs=64):
+    t0 = time.time()
+    nodes, members, k, cons, loads = truss.lattice_truss(n, n_rhs)
+    t_gen = time.time() - t0
+    nd, mem = core.to_device(nodes, torch.float64), core.to_device(members, torch.int32)
+    kd = core.to_device(k, torch.float64)
+    fixed = core._fixed_mask(cons, nodes.size)
+    B = core.to_device(loads, torch.float64)
+    for _ in range(2):
+        pat = core.symbolic(mem, nodes.shape[0])
+        K = core.assemble_truss(nd, mem, kd, pattern=pat, fixed=fixed)
+    pat, ms_sym = timed(lambda: core.symbolic(mem, nodes.shape[0]), 3)
+    K, ms_num = timed(lambda: core.assemble_truss(nd, mem, kd, pattern=pat, fixed=fixed), 5)
+    _, ms_ke = timed(lambda: truss.member_stiffness_matrices(nd, mem, kd), 5)
+    K.matmat(B)
+    Y, ms_spmm = timed(lambda: K.matmat(B), 5)
+    (X, info), ms_solve = timed(lambda: core.pcg_multi(K, B, tol=1e-12, raise_on_failure=False))
+    # true residual of every column over the free DOF
+    R = B - K.matmat(X)
+    free = (fixed == 0)
+    rel = (R[free].norm(dim=0) / B[free].norm(dim=0)).max().item()
+    n_dof, M = K.n_dof, members.shape[0]
+    print(json.dumps({"config": 5, "workload": f"lattice space truss n={n}, {n_rhs} load cases", "nodes": nodes.shape[0],
+                      "dof": n_dof, "members": int(M), "nnz": K.nnz, "host_generation_s": t_gen,
+                      "ms": {"symbolic": ms_sym, "numeric": ms_num, "ke_materialised": ms_ke, "spmm": ms_spmm,
+                             "solve": ms_solve, "pcg_iteration": ms_solve / max(info.iterations, 1)},
+                      "elem_per_s": {"symbolic": M / ms_sym * 1e3, "numeric_incl_ke": M / ms_num * 1e3,
+                                     "ke_materialised": M / ms_ke * 1e3},
+                      "spmm_gb_per_s_algorithmic": (12 * K.nnz + 4 * n_dof + 16 * n_dof * n_rhs) / ms_spmm / 1e6,
+                      "pcg": {"iterations_total": info.iterations, "iterations_per_column_min": int(info.history.min()),
+                              "iterations_per_column_max": int(info.history.max()), "status": info.status,
+                              "recurrence_rel_residual_worst": info.rel_residual, "true_rel_residual_worst": rel},
+                      "solved_dof_columns_per_s": int(free.sum()) * n_rhs / (ms_sym + ms_num + ms_solve) * 1e3}))
+
+
+if __name__ == "__main__":
+    which = [a for a in sys.argv[1:] if a in ("2", "3", "5")] or ["2", "3", "5"]
+    n_lat = int(sys.argv[sys.argv.index("--lattice") + 1]) if "--lattice" in sys.argv else 93
+    if "2" in which:
+        config2()
+    if "3" in which:
+        config3()
+    if "5" in which:
+        config5(n_lat)
