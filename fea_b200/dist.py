@@ -180,9 +180,9 @@ def distributed_pcg(ops, plan: SlabPlan, d: int, b_owned: torch.Tensor, dinv_own
     events = [torch.cuda.Event() for _ in range(2)] if dev.type == "cuda" else None
     pending = [False, False]
     done_iter, slot, finished = 0, 0, False
-    while not finished:
-        todo = min(chunk, max_iter - done_iter)
-        for _ in range(todo):
+
+    def run_iterations(count: int) -> None:
+        for _ in range(count):
             halo(p_ext)
             ops.step_spmv(p_ext, ap, state)
             if multi:
@@ -191,6 +191,35 @@ def distributed_pcg(ops, plan: SlabPlan, d: int, b_owned: torch.Tensor, dinv_own
             if multi:
                 dist.all_reduce(state[_lib.PCG_RZ_NEW:_lib.PCG_RR + 1], group=group)
             ops.step_direction(dinv_owned, r, p_own, state)
+
+    # On GPUs a chunk of iterations (kernels + NCCL send/recv + all-reduces, all with fixed
+    # arguments) is captured once into a CUDA graph and replayed: at 8 ranks a rank's kernels take
+    # ~0.13 ms per iteration, less than the host needs to issue 3 launches and 3 collectives.
+    graph = None
+    # Off by default: measured at 2 ranks the captured NCCL ops cost ~90 us more per iteration than
+    # plain launches (5.5 s vs 4.8 s per solve); it only pays when a rank is host-bound.
+    if dev.type == "cuda" and max_iter > chunk and os.environ.get("FEA_DIST_GRAPH", "0") == "1":
+        run_iterations(1)  # warm-up outside capture (lazy NCCL / kernel-attribute initialisation)
+        done_iter += 1
+        torch.cuda.synchronize()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run_iterations(chunk)
+            graph = g
+        except Exception as exc:  # capture unsupported in this setup: plain launches
+            if plan.rank == 0:
+                print(f"fea_b200.dist: CUDA-graph capture failed ({type(exc).__name__}: {exc}); using plain launches",
+                      flush=True)
+            graph = None
+            torch.cuda.synchronize()
+
+    while not finished:
+        todo = min(chunk, max_iter - done_iter)
+        if graph is not None and todo == chunk:
+            graph.replay()
+        else:
+            run_iterations(todo)
         done_iter += todo
         snap[slot].copy_(state, non_blocking=True)
         if events is not None:
