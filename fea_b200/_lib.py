@@ -45,6 +45,23 @@ class PcgResult(ctypes.Structure):
     ]
 
 
+FEA_ERR_PEER = 8
+MAX_PEERS = 8
+
+
+class PeerComm(ctypes.Structure):
+    """fea_peer_comm of include/fea_b200.h."""
+
+    _fields_ = [
+        ("world", c_int32), ("rank", c_int32), ("lower_peer", c_int32), ("upper_peer", c_int32),
+        ("comm", c_void_p * MAX_PEERS),
+        ("own_offset_nodes", c_int64),
+        ("send_lower_first", c_int64), ("send_lower_count", c_int64), ("send_lower_dst", c_int64),
+        ("send_upper_first", c_int64), ("send_upper_count", c_int64), ("send_upper_dst", c_int64),
+        ("epoch", c_int64),
+    ]
+
+
 P = c_void_p  # every device / host pointer crosses the ABI as a plain address
 
 # name -> (restype, argtypes); mirrors include/fea_b200.h one to one
@@ -75,6 +92,14 @@ PROTOTYPES = {
     "fea_pcg_step_spmv": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, c_int64, P, P, P]),
     "fea_pcg_step_update": (c_int32, [c_int64, P, P, P, P, P, P, P, P]),
     "fea_pcg_step_direction": (c_int32, [c_int64, P, P, P, P, P, P]),
+    "fea_comm_bytes": (c_size_t, [c_int64]),
+    "fea_comm_alloc": (c_int32, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "fea_comm_free": (c_int32, [P]),
+    "fea_comm_ipc_export": (c_int32, [P, P]),
+    "fea_comm_ipc_open": (c_int32, [P, ctypes.POINTER(c_void_p)]),
+    "fea_comm_ipc_close": (c_int32, [P]),
+    "fea_pcg_solve_p2p": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, P, c_double, c_int32, P, c_size_t,
+                                    ctypes.POINTER(PeerComm), ctypes.POINTER(PcgResult), P]),
     "fea_pcg_multi_workspace": (c_size_t, [c_int64, c_int32]),
     "fea_pcg_solve_multi": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, c_int32, c_double, c_int32, P, c_size_t,
                                       P, ctypes.POINTER(PcgResult), P]),

@@ -1,0 +1,365 @@
+// Multi-GPU Jacobi-PCG over NVLink peer memory, without NCCL in the iteration.
+//
+// The slab partition (fea_b200/dist.py) needs, per PCG iteration, one halo exchange of
+// p with the two z-neighbours (157 KB each at 400x80x80) and two tiny all-reduces.  Through NCCL
+// that is three collectives of ~15-20 us each per iteration, issued by the host; at 8 ranks a rank's
+// kernels only take ~0.13 ms per iteration, so latency dominates.  Here every rank maps its peers'
+// communication blocks (CUDA IPC, NVSwitch gives every pair full bandwidth) and the exchange is
+// done by three tiny kernels per iteration that live in the same stream / CUDA graph as the
+// solver kernels:
+//
+//   p2p_halo_kernel       push my boundary layer of p straight into the neighbours' halo rows
+//                         (coalesced remote stores), release-store an iteration tag into their
+//                         header, then wait for the neighbours' tags           (~6 us)
+//   p2p_allreduce_kernel  one warp: lane r stores this rank's partial sum(s) + tag into rank r's
+//                         slot array, then waits for rank r's slot in the own array; lane 0 adds the
+//                         world values in rank order -- every rank gets the bitwise identical sum,
+//                         deterministic, no atomics                           (~4 us)
+//
+// Tags are (epoch << 32 | iteration + 1), slots are double-buffered by iteration parity; a rank can
+// never be two exchanges ahead of a peer because every exchange needs every rank's contribution.
+// Spins are bounded: a peer that never arrives raises FEA_ERR_PEER instead of hanging the GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "pcg_common.cuh"
+
+namespace fea {
+
+constexpr int kMaxPeers = FEA_MAX_PEERS;
+constexpr size_t kCommHeaderBytes = 4096;
+
+struct PeerSlot {
+  double v[2];
+  long long tag;
+  long long pad;
+};
+struct CommHeader {
+  PeerSlot slots[2][3][kMaxPeers];  // [parity][kind][source rank]
+  long long halo_tag[2];            // [0] written by the lower neighbour, [1] by the upper one
+  unsigned int counter;             // last-block ticket of the halo kernel
+  int error;
+};
+static_assert(sizeof(CommHeader) <= kCommHeaderBytes, "comm header");
+
+struct PeerView {  // kernel argument
+  int world, rank, lower, upper;
+  CommHeader* hdr[kMaxPeers];
+  double* lower_dst;
+  double* upper_dst;
+  const double* lower_src;
+  const double* upper_src;
+  long long lower_cnt, upper_cnt;
+  long long epoch;
+};
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded spin (about 2 s): true when *p reaches `want` (exactly, or at least with `at_least`).
+__device__ __forceinline__ bool spin_until(const long long* p, long long want, bool at_least) {
+  for (int i = 0; i < (1 << 24); ++i) {
+    const long long v = ld_acquire_sys(p);
+    if (at_least ? v >= want : v == want) return true;
+    __nanosleep(100);
+  }
+  return false;
+}
+__device__ __forceinline__ void peer_failure(const PeerView& pv, PcgState* st) {
+  pv.hdr[pv.rank]->error = 1;
+  st->status = FEA_ERR_PEER;
+  st->done = 1;
+  st->rr_final = st->rr;
+}
+
+// kind 0: (rz, bnorm2) after init; kind 1: pap after step 1; kind 2: (rz_new, rr) after step 2.
+__global__ void __launch_bounds__(32) p2p_allreduce_kernel(PeerView pv, PcgState* st, int kind) {
+  if (st->done) return;
+  const int lane = threadIdx.x;
+  // iteration this exchange belongs to: step 2 has already incremented st->iter
+  const long long k = kind == 2 ? st->iter - 1 : st->iter;
+  const long long tag = (pv.epoch << 32) | (k + 1);
+  const int parity = (int)(k & 1);
+  double mine0, mine1;
+  if (kind == 0) {
+    mine0 = st->rz;
+    mine1 = st->bnorm2;
+  } else if (kind == 1) {
+    mine0 = st->pap;
+    mine1 = 0.0;
+  } else {
+    mine0 = st->rz_new;
+    mine1 = st->rr;
+  }
+  if (lane < pv.world) {
+    PeerSlot* dst = &pv.hdr[lane]->slots[parity][kind][pv.rank];
+    dst->v[0] = mine0;
+    dst->v[1] = mine1;
+    __threadfence_system();
+    st_release_sys(&dst->tag, tag);
+  }
+  double v0 = 0.0, v1 = 0.0;
+  bool ok = true;
+  if (lane < pv.world) {
+    const PeerSlot* src = &pv.hdr[pv.rank]->slots[parity][kind][lane];
+    ok = spin_until(&src->tag, tag, false);
+    v0 = ld_volatile_f64(&src->v[0]);
+    v1 = ld_volatile_f64(&src->v[1]);
+  }
+  const bool all_ok = __all_sync(kFull, ok);
+  double s0 = 0.0, s1 = 0.0;
+  for (int r = 0; r < pv.world; ++r) {  // rank order: identical sums on every rank
+    s0 += __shfl_sync(kFull, v0, r);
+    s1 += __shfl_sync(kFull, v1, r);
+  }
+  if (lane == 0) {
+    if (!all_ok) {
+      peer_failure(pv, st);
+    } else if (kind == 0) {
+      st->rz = s0;
+      st->bnorm2 = s1;
+      st->rr = s1;
+    } else if (kind == 1) {
+      st->pap = s0;
+    } else {
+      st->rz_new = s0;
+      st->rr = s1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) p2p_halo_kernel(PeerView pv, PcgState* st) {
+  __shared__ bool s_last;
+  if (st->done) return;
+  const long long tag = (pv.epoch << 32) | ((long long)st->iter + 1);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pv.lower >= 0)
+    for (long long i = tid; i < pv.lower_cnt; i += stride) pv.lower_dst[i] = pv.lower_src[i];
+  if (pv.upper >= 0)
+    for (long long i = tid; i < pv.upper_cnt; i += stride) pv.upper_dst[i] = pv.upper_src[i];
+  __threadfence_system();
+  __syncthreads();
+  CommHeader* own = pv.hdr[pv.rank];
+  if (threadIdx.x == 0) s_last = atomicAdd(&own->counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  own->counter = 0;
+  __threadfence_system();
+  if (pv.lower >= 0) st_release_sys(&pv.hdr[pv.lower]->halo_tag[1], tag);  // I am its upper neighbour
+  if (pv.upper >= 0) st_release_sys(&pv.hdr[pv.upper]->halo_tag[0], tag);
+  bool ok = true;
+  if (pv.lower >= 0) ok = spin_until(&own->halo_tag[0], tag, true) && ok;
+  if (pv.upper >= 0) ok = spin_until(&own->halo_tag[1], tag, true) && ok;
+  if (!ok) peer_failure(pv, st);
+}
+
+}  // namespace fea
+
+using namespace fea;
+
+extern "C" size_t fea_comm_bytes(int64_t n_local_dof) {
+  return kCommHeaderBytes + align_up(sizeof(double) * (size_t)n_local_dof, 256);
+}
+
+extern "C" int fea_comm_alloc(size_t bytes, void** out) {
+  if (!out || bytes < kCommHeaderBytes) return FEA_ERR_INVALID;
+  FEA_TRY(check(cudaMalloc(out, bytes)));
+  return check(cudaMemset(*out, 0, bytes));
+}
+
+extern "C" int fea_comm_free(void* ptr) { return check(cudaFree(ptr)); }
+
+extern "C" int fea_comm_ipc_export(void* ptr, unsigned char* handle64) {
+  if (!ptr || !handle64) return FEA_ERR_INVALID;
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  FEA_TRY(check(cudaIpcGetMemHandle(&h, ptr)));
+  std::memcpy(handle64, &h, 64);
+  return FEA_OK;
+}
+
+extern "C" int fea_comm_ipc_open(const unsigned char* handle64, void** out) {
+  if (!handle64 || !out) return FEA_ERR_INVALID;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  return check(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+}
+
+extern "C" int fea_comm_ipc_close(void* ptr) { return check(cudaIpcCloseMemHandle(ptr)); }
+
+extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t* node_rowptr_owned,
+                                 const int32_t* node_colidx, const double* values, int32_t max_coupled,
+                                 const double* dinv, const double* b, double* x, double tol, int32_t max_iter,
+                                 void* work, size_t work_bytes, const fea_peer_comm* comm,
+                                 fea_pcg_result* result_host, void* stream_) {
+  cudaStream_t caller = static_cast<cudaStream_t>(stream_);
+  if (!node_rowptr_owned || !node_colidx || !values || !dinv || !b || !x || !work || !comm || !result_host)
+    return FEA_ERR_INVALID;
+  if (n_owned_nodes <= 0 || d < 1 || d > 3 || max_iter < 1) return FEA_ERR_INVALID;
+  if (comm->world < 1 || comm->world > kMaxPeers || comm->rank < 0 || comm->rank >= comm->world) return FEA_ERR_INVALID;
+  const int64_t n = n_owned_nodes * d;
+  if (work_bytes < fea_pcg_workspace(n)) return FEA_ERR_WORKSPACE;
+
+  // workspace: state | partials | r | (p lives in the comm block) | ap
+  char* c = static_cast<char*>(work);
+  PcgState* state = reinterpret_cast<PcgState*>(c);
+  c += FEA_PCG_STATE_BYTES;
+  double* partials = reinterpret_cast<double*>(c);
+  c += sizeof(double) * 2 * kMaxPartials;
+  const size_t vec = align_up(sizeof(double) * (size_t)n, 256);
+  double* r = reinterpret_cast<double*>(c);
+  c += vec;
+  double* ap = reinterpret_cast<double*>(c);
+
+  PeerView pv;
+  std::memset(&pv, 0, sizeof(pv));
+  pv.world = comm->world;
+  pv.rank = comm->rank;
+  pv.lower = comm->lower_peer;
+  pv.upper = comm->upper_peer;
+  pv.epoch = comm->epoch;
+  for (int i = 0; i < comm->world; ++i) {
+    if (!comm->comm[i]) return FEA_ERR_INVALID;
+    pv.hdr[i] = static_cast<CommHeader*>(comm->comm[i]);
+  }
+  auto p_ext_of = [&](int rank) {
+    return reinterpret_cast<double*>(static_cast<char*>(comm->comm[rank]) + kCommHeaderBytes);
+  };
+  double* p_ext = p_ext_of(comm->rank);
+  double* p_own = p_ext + comm->own_offset_nodes * d;
+  if (pv.lower >= 0) {
+    pv.lower_src = p_own + comm->send_lower_first * d;
+    pv.lower_cnt = comm->send_lower_count * d;
+    pv.lower_dst = p_ext_of(pv.lower) + comm->send_lower_dst * d;
+  }
+  if (pv.upper >= 0) {
+    pv.upper_src = p_own + comm->send_upper_first * d;
+    pv.upper_cnt = comm->send_upper_count * d;
+    pv.upper_dst = p_ext_of(pv.upper) + comm->send_upper_dst * d;
+  }
+  const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_owned_nodes);
+
+  PcgState* snap = nullptr;
+  FEA_TRY(check(cudaMallocHost(&snap, 2 * sizeof(PcgState))));
+  cudaEvent_t ev[2] = {nullptr, nullptr}, ev_order = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int rc = check(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  if (rc == FEA_OK) rc = check(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  if (rc == FEA_OK) rc = check(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
+  if (rc == FEA_OK) rc = check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  if (rc == FEA_OK) rc = check(cudaEventRecord(ev_order, caller));
+  if (rc == FEA_OK) rc = check(cudaStreamWaitEvent(stream, ev_order, 0));
+
+  const unsigned vb = vec_blocks(n);
+  const bool multi = comm->world > 1;
+  const unsigned halo_blocks = 8;
+  auto exchange = [&](int kind) {
+    if (multi) p2p_allreduce_kernel<<<1, 32, 0, stream>>>(pv, state, kind);
+  };
+  auto halo = [&]() {
+    if (multi) p2p_halo_kernel<<<halo_blocks, 256, 0, stream>>>(pv, state);
+  };
+  auto iteration = [&]() -> int {
+    const int r1 = pcg_step_spmv(d, n_owned_nodes, node_rowptr_owned, node_colidx, values, p_ext, ap,
+                                 comm->own_offset_nodes, state, partials, stream, &plan);
+    exchange(1);
+    pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials);
+    exchange(2);
+    pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, nullptr);
+    halo();
+    return r1;
+  };
+  const int launches_per_iteration = multi ? 6 : 3;
+
+  if (rc == FEA_OK) {
+    pcg_match_carveout();
+    rc = check(cudaMemsetAsync(state, 0, FEA_PCG_STATE_BYTES, stream));
+  }
+  if (rc == FEA_OK) {
+    pcg_init_kernel<<<vb, 256, 0, stream>>>(n, b, dinv, x, r, p_own, tol, max_iter, state, partials);
+    exchange(0);
+    halo();
+    rc = check_launch(multi ? 3 : 1);
+  }
+  const int chunk = 32;
+  int enqueued = 0, slot = 0;
+  bool pending[2] = {false, false};
+  bool finished = false;
+  if (rc == FEA_OK && max_iter >= chunk && std::getenv("FEA_PCG_NO_GRAPH") == nullptr) {
+    rc = iteration();  // warm-up outside capture
+    if (rc == FEA_OK) rc = check_launch(launches_per_iteration);
+    enqueued += 1;
+    cudaGraph_t graph = nullptr;
+    if (rc == FEA_OK && cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      for (int it = 0; it < chunk; ++it) iteration();
+      if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || graph == nullptr ||
+          cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess)
+        graph_exec = nullptr;
+      if (graph != nullptr) cudaGraphDestroy(graph);
+    }
+    cudaGetLastError();
+  }
+  while (rc == FEA_OK && !finished) {
+    const int todo = std::min(chunk, max_iter - enqueued);
+    if (graph_exec != nullptr && todo == chunk) {
+      rc = check(cudaGraphLaunch(graph_exec, stream));
+    } else {
+      for (int it = 0; it < todo && rc == FEA_OK; ++it) rc = iteration();
+    }
+    if (rc == FEA_OK) rc = check_launch(launches_per_iteration * todo);
+    if (rc != FEA_OK) break;
+    enqueued += todo;
+    rc = check(cudaMemcpyAsync(&snap[slot], state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+    if (rc != FEA_OK) break;
+    rc = check(cudaEventRecord(ev[slot], stream));
+    if (rc != FEA_OK) break;
+    pending[slot] = true;
+    const int prev = slot ^ 1;
+    if (pending[prev]) {
+      rc = check(cudaEventSynchronize(ev[prev]));
+      pending[prev] = false;
+      if (rc == FEA_OK && snap[prev].done) finished = true;
+    }
+    if (!finished && enqueued >= max_iter) finished = true;
+    slot ^= 1;
+  }
+  if (rc == FEA_OK) {
+    rc = check(cudaMemcpyAsync(&snap[0], state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+    if (rc == FEA_OK) rc = check(cudaStreamSynchronize(stream));
+  }
+  if (rc == FEA_OK) {
+    const PcgState& s = snap[0];
+    result_host->iterations = s.iter;
+    result_host->status = s.status;
+    if (!s.done && s.status == FEA_OK) result_host->status = FEA_ERR_MAXITER;
+    result_host->bnorm = std::sqrt(s.bnorm2);
+    const double rr = s.done ? s.rr_final : s.rr;
+    result_host->rel_residual = s.bnorm2 > 0.0 ? std::sqrt(rr / s.bnorm2) : 0.0;
+    profile().pcg_iterations += s.iter;
+  } else if (stream != nullptr) {
+    cudaStreamSynchronize(stream);
+  }
+  if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
+  if (stream != nullptr) {
+    if (ev_order != nullptr && cudaEventRecord(ev_order, stream) == cudaSuccess) cudaStreamWaitEvent(caller, ev_order, 0);
+    cudaStreamDestroy(stream);
+  }
+  for (cudaEvent_t e : {ev[0], ev[1], ev_order})
+    if (e != nullptr) cudaEventDestroy(e);
+  cudaFreeHost(snap);
+  return rc;
+}

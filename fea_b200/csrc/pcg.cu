@@ -22,7 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "spmv_tma.cuh"
+#include "pcg_common.cuh"
 
 namespace fea {
 
@@ -71,26 +71,6 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
   plan.ok = true;
   return plan;
 }
-
-// Device-resident solver state (FEA_PCG_STATE_BYTES = 256 bytes).
-struct PcgState {
-  double rz;       // FEA_PCG_RZ      r.z of the current iterate
-  double bnorm2;   // FEA_PCG_BNORM2  ||b||^2 over free DOF
-  double rz_new;   // FEA_PCG_RZ_NEW
-  double rr;       // FEA_PCG_RR      ||r||^2 over free DOF
-  double pap;      // FEA_PCG_PAP
-  double tol2;     // FEA_PCG_TOL2
-  double rr_final; // FEA_PCG_RR_FINAL  ||r||^2 frozen when `done` is set (later no-op steps of a
-                   //                   multi-rank driver keep all-reducing the live scalars)
-  double spare[9];
-  int32_t iter;      // int32 index 32
-  int32_t done;      // 33
-  int32_t status;    // 34
-  int32_t max_iter;  // 35
-  uint32_t counter[4];
-  int32_t pad[24];
-};
-static_assert(sizeof(PcgState) == FEA_PCG_STATE_BYTES, "PcgState layout");
 
 // Block partial -> global slot; returns true in the last block to finish (all threads).
 __device__ __forceinline__ bool publish_partials(double* partials, int n_scalars, const double* vals,
@@ -420,10 +400,6 @@ pcg_init_kernel(int64_t n, const double* __restrict__ b, const double* __restric
   }
 }
 
-inline unsigned vec_blocks(int64_t n) {
-  // 8 resident CTAs of 256 threads per SM, one full wave (<= kMaxPartials blocks)
-  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 4), 148LL * 8));
-}
 inline unsigned spmv_blocks(int64_t n_nodes) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_nodes, kSpmvWarps), 148LL * 8));
 }
@@ -435,8 +411,6 @@ struct PcgWork {
   double* p;
   double* ap;
 };
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static PcgWork carve_pcg(void* work, int64_t n) {
   PcgWork w;
@@ -463,9 +437,9 @@ static int launch_step_spmv(int64_t n_nodes, const int32_t* rp, const int32_t* c
   return FEA_OK;
 }
 
-static int step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
-                     const double* p, double* ap, int64_t off, PcgState* st, double* partials, cudaStream_t stream,
-                     const TmaPlan* plan = nullptr) {
+int pcg_step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
+                  const double* p, double* ap, int64_t off, PcgState* st, double* partials, cudaStream_t stream,
+                  const TmaPlan* plan) {
   if (plan != nullptr && plan->ok)
     return dispatch_tma(d, *plan, true, n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
   switch (d) {
@@ -510,7 +484,7 @@ extern "C" size_t fea_pcg_workspace(int64_t n_dof) {
 // an SM reconfiguration (~25 us per launch measured at 100x20x20, where a whole iteration is
 // otherwise ~35 us), so the vector kernels ask for the SpMV's carve-out: they stream and do not
 // need L1.
-static void match_carveout() {
+void fea::pcg_match_carveout() {
   static bool done = false;
   if (done) return;
   done = true;
@@ -524,7 +498,7 @@ extern "C" int fea_pcg_init(int64_t n_dof, const double* b, const double* dinv, 
                             double tol, int32_t max_iter, void* state, void* partials, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!b || !dinv || !x || !r || !p || !state || !partials || n_dof <= 0) return FEA_ERR_INVALID;
-  match_carveout();
+  pcg_match_carveout();
   FEA_TRY(check(cudaMemsetAsync(state, 0, FEA_PCG_STATE_BYTES, stream)));
   pcg_init_kernel<<<vec_blocks(n_dof), 256, 0, stream>>>(n_dof, b, dinv, x, r, p, tol, max_iter,
                                                         static_cast<PcgState*>(state), static_cast<double*>(partials));
@@ -538,7 +512,7 @@ extern "C" int fea_pcg_step_spmv(int64_t n_owned_nodes, int32_t d, const int32_t
   if (!node_rowptr || !node_colidx || !values || !p || !ap || !state || !partials || n_owned_nodes <= 0)
     return FEA_ERR_INVALID;
   const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_owned_nodes);
-  FEA_TRY(step_spmv(d, n_owned_nodes, node_rowptr, node_colidx, values, p, ap, p_row_offset,
+  FEA_TRY(pcg_step_spmv(d, n_owned_nodes, node_rowptr, node_colidx, values, p, ap, p_row_offset,
                     static_cast<PcgState*>(state), static_cast<double*>(partials),
                     static_cast<cudaStream_t>(stream_), &plan));
   return check_launch();
@@ -621,7 +595,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   auto enqueue_iteration = [&](bool sample) -> int {
     if (sample) sample_iter[n_samples] = enqueued;  // 0-based index of the iteration being timed
     if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
-    const int r = step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream,
+    const int r = pcg_step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream,
                             &plan);
     if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
     pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials);

@@ -298,6 +298,90 @@ class GpuOps:
                                      x_ext.data_ptr(), y_owned.data_ptr(), self.core._stream()), "fea_spmv")
 
 
+class P2PComm:
+    """This rank's communication block (header + halo-extended p vector) and the IPC mappings of
+    every peer's block, for fea_pcg_solve_p2p.  Cached per slab plan: allocation and the handle
+    exchange happen once, later solves only bump the epoch."""
+
+    _cache: dict = {}
+
+    @classmethod
+    def get(cls, plan: SlabPlan, d: int, group=None) -> "P2PComm":
+        key = (plan.rank, plan.world, plan.own_lo, plan.own_hi, plan.g_lo, plan.g_hi, d)
+        if key not in cls._cache:
+            cls._cache[key] = cls(plan, d, group)
+        return cls._cache[key]
+
+    def __init__(self, plan: SlabPlan, d: int, group=None):
+        import ctypes
+
+        lib = _lib.load()
+        self.lib, self.plan, self.d, self.epoch = lib, plan, d, 0
+        nbytes = lib.fea_comm_bytes(plan.n_local * d)
+        own = ctypes.c_void_p()
+        _lib.check(lib.fea_comm_alloc(nbytes, ctypes.byref(own)), "fea_comm_alloc")
+        self.own = own.value
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.fea_comm_ipc_export(self.own, ctypes.addressof(handle)), "fea_comm_ipc_export")
+        infos = [None] * plan.world
+        dist.all_gather_object(infos, (bytes(handle), plan.g_lo), group=group)
+        self.ptrs, self.g_los = [], [g for _, g in infos]
+        for r, (h, _) in enumerate(infos):
+            if r == plan.rank:
+                self.ptrs.append(self.own)
+                continue
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            p = ctypes.c_void_p()
+            _lib.check(lib.fea_comm_ipc_open(ctypes.addressof(buf), ctypes.byref(p)), "fea_comm_ipc_open")
+            self.ptrs.append(p.value)
+        dist.barrier(group=group)  # every block is mapped everywhere before anyone writes
+
+    def descriptor(self) -> "_lib.PeerComm":
+        pl = self.plan
+        self.epoch += 1
+        c = _lib.PeerComm()
+        c.world, c.rank = pl.world, pl.rank
+        c.lower_peer = pl.send_down[0] if pl.send_down is not None else -1
+        c.upper_peer = pl.send_up[0] if pl.send_up is not None else -1
+        for r, p in enumerate(self.ptrs):
+            c.comm[r] = p
+        c.own_offset_nodes = pl.offset
+        if pl.send_down is not None:
+            peer, lo, hi = pl.send_down
+            c.send_lower_first, c.send_lower_count, c.send_lower_dst = lo - pl.own_lo, hi - lo, lo - self.g_los[peer]
+        if pl.send_up is not None:
+            peer, lo, hi = pl.send_up
+            c.send_upper_first, c.send_upper_count, c.send_upper_dst = lo - pl.own_lo, hi - lo, lo - self.g_los[peer]
+        c.epoch = self.epoch
+        return c
+
+
+def p2p_pcg(K, plan: SlabPlan, b_owned: torch.Tensor, dinv_owned: torch.Tensor, tol: float, max_iter: int, group=None):
+    """Distributed Jacobi-PCG through fea_pcg_solve_p2p (NVLink peer memory, no NCCL per iteration)."""
+    import ctypes
+
+    from . import core
+
+    lib = _lib.load()
+    d = K.dof_per_node
+    comm = P2PComm.get(plan, d, group)
+    desc = comm.descriptor()
+    n = plan.n_owned * d
+    x = torch.empty(n, dtype=torch.float64, device=b_owned.device)
+    ws_bytes = lib.fea_pcg_workspace(n)
+    work = torch.empty(ws_bytes, dtype=torch.uint8, device=b_owned.device)
+    rowptr_owned = K.pattern.node_rowptr[plan.offset:]
+    res = _lib.PcgResult()
+    pt = K.pattern
+    _lib.check(lib.fea_pcg_solve_p2p(plan.n_owned, d, rowptr_owned.data_ptr(), pt.node_colidx.data_ptr(),
+                                     K.values.data_ptr(), pt.max_coupled, dinv_owned.data_ptr(), b_owned.data_ptr(),
+                                     x.data_ptr(), float(tol), int(max_iter), work.data_ptr(), ws_bytes,
+                                     ctypes.byref(desc), ctypes.byref(res), core._stream()), "fea_pcg_solve_p2p")
+    if res.status == _lib.FEA_ERR_PEER:
+        raise _lib.FeaLibraryError("fea_pcg_solve_p2p: a peer rank never delivered its halo / partial sum")
+    return x, DistInfo(res.iterations, res.rel_residual, res.status, res.bnorm)
+
+
 def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan, tol=1e-12, max_iter=None,
                     group=None):
     """This rank's share of solve(nodes, elements, constraints, forces) (cubebeam.py:79-108).
@@ -318,7 +402,11 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
     ops = GpuOps(K, plan)
     if max_iter is None:
         max_iter = 10 * 3 * int(np.asarray(nodes).shape[0])
-    x, info = distributed_pcg(ops, plan, 3, b_owned, dinv_owned, tol=tol, max_iter=max_iter, group=group)
+    # NVLink peer-memory solver by default; FEA_DIST_COMM=nccl selects the torch.distributed loop
+    if plan.world > 1 and os.environ.get("FEA_DIST_COMM", "p2p") == "p2p":
+        x, info = p2p_pcg(K, plan, b_owned, dinv_owned, tol, max_iter, group=group)
+    else:
+        x, info = distributed_pcg(ops, plan, 3, b_owned, dinv_owned, tol=tol, max_iter=max_iter, group=group)
     # reactions: K_full u on the owned rows needs u on the halo
     u_ext = torch.zeros(3 * plan.n_local, dtype=torch.float64, device=x.device)
     u_ext[lo:hi] = x

@@ -38,7 +38,8 @@ enum {
   FEA_ERR_BREAKDOWN = 4, /* PCG p.Ap <= 0: K_ff not positive definite (cubebeam.py:98 -> LinAlgError) */
   FEA_ERR_MAXITER = 5,   /* PCG hit max_iter before the tolerance */
   FEA_ERR_WORKSPACE = 6, /* caller workspace too small */
-  FEA_ERR_DEGENERATE = 7 /* zero-length truss member */
+  FEA_ERR_DEGENERATE = 7, /* zero-length truss member */
+  FEA_ERR_PEER = 8        /* multi-GPU: a peer rank never delivered its halo / partial sum */
 };
 
 /* Library / build identification ("fea_b200 <version> sm_100a"). */
@@ -225,6 +226,45 @@ int fea_pcg_step_update(int64_t n_dof, const double* dinv, const double* p, cons
 /* history, may be NULL: device array [max_iter], entry it-1 receives ||r||/||b|| of iteration it. */
 int fea_pcg_step_direction(int64_t n_dof, const double* dinv, const double* r, double* p,
                            void* state, double* history, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3b) Multi-GPU Jacobi-PCG over NVLink peer memory (one process per GPU, 1-D slab partition).
+ *      Every rank allocates one communication block (header + its halo-extended p vector) with
+ *      fea_comm_alloc, exports it with fea_comm_ipc_export, and maps its peers' blocks with
+ *      fea_comm_ipc_open (CUDA IPC; the 64-byte handles travel through any host channel, e.g.
+ *      torch.distributed.all_gather_object).  fea_pcg_solve_p2p then runs the whole iteration --
+ *      halo push into the neighbours' memory, one-shot all-reduces of the dot products, the three
+ *      solver kernels -- as one CUDA graph per 32 iterations, without NCCL.
+ * ---------------------------------------------------------------------------------------- */
+#define FEA_MAX_PEERS 8
+typedef struct {
+  int32_t world, rank;
+  int32_t lower_peer, upper_peer;  /* neighbour ranks, -1 if none */
+  void* comm[FEA_MAX_PEERS];       /* comm[r]: rank r's block as mapped in this process (comm[rank] = own) */
+  int64_t own_offset_nodes;        /* owned rows start at this node of the local (halo-extended) range */
+  /* my owned nodes [first, first+count) (relative to the first owned node) go to node `dst` of the
+   * neighbour's local range */
+  int64_t send_lower_first, send_lower_count, send_lower_dst;
+  int64_t send_upper_first, send_upper_count, send_upper_dst;
+  int64_t epoch;                   /* distinct for every solve that reuses the blocks (same on all ranks) */
+} fea_peer_comm;
+
+size_t fea_comm_bytes(int64_t n_local_dof);
+int fea_comm_alloc(size_t bytes, void** out);  /* cudaMalloc + zero */
+int fea_comm_free(void* ptr);
+int fea_comm_ipc_export(void* ptr, unsigned char* handle64_host);
+int fea_comm_ipc_open(const unsigned char* handle64_host, void** out);
+int fea_comm_ipc_close(void* ptr);
+
+/* Arguments as fea_pcg_solve, restricted to this rank's owned rows: node_rowptr_owned points at
+ * the first owned node's entry of the slab's node_rowptr (entries stay absolute), dinv / b / x have
+ * n_owned_nodes * dof_per_node entries.  Synchronises; identical result on every rank.
+ * result_host->status may also be FEA_ERR_PEER (a peer never arrived). */
+int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t dof_per_node, const int32_t* node_rowptr_owned,
+                      const int32_t* node_colidx, const double* values, int32_t max_coupled,
+                      const double* dinv, const double* b, double* x, double tol, int32_t max_iter,
+                      void* work, size_t work_bytes, const fea_peer_comm* comm,
+                      fea_pcg_result* result_host, void* stream);
 
 /* Batched multi-RHS Jacobi-PCG (BASELINE config 5): n_rhs <= 256 independent systems sharing K,
  * each column with its own alpha/beta and stopping rule.  B, X: (n_dof, n_rhs) row-major.
