@@ -495,7 +495,10 @@ def bench_entry(args, A, b, tol, E, nu, measured_peaks, ClockSampler, cpu_sample
                        "free_dof": n_free, "elements": int(elements.shape[0]), "tol": tol,
                        "pcg_iterations": info.iterations, "rel_residual": info.rel_residual,
                        "preconditioner": "jacobi",
-                       "parallelism": f"{world} z-slabs, NCCL halo send/recv + all-reduced dots",
+                       "parallelism": (f"{world} z-slabs, NVLink peer-memory halo push + one-shot all-reduce "
+                                       "kernels inside the solver's CUDA graph (no NCCL per iteration)"
+                                       if os.environ.get("FEA_DIST_COMM", "p2p") == "p2p" else
+                                       f"{world} z-slabs, NCCL halo send/recv + all-reduced dots"),
                        "l2": "per-rank CSR slab larger than L2 for N <= 8; no flush"},
             "roofline": {"kernel": "spmv_kernel<3> on the rank's slab (timed alone after the steps)", "bound": "hbm",
                          "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak,

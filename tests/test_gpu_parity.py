@@ -399,3 +399,42 @@ def test_config4_assembly_properties(mods):
     z = K.matvec(2.0 * x - 3.0 * y)
     assert float((z - (2.0 * Kx - 3.0 * Ky)).abs().max()) < 1e-12 * float(Kx.abs().max())
     assert float(x @ Kx) > 0
+
+
+def test_p2p_solver_single_rank(mods):
+    """fea_pcg_solve_p2p with world = 1 (no peers): exercises the comm block API, the private
+    stream / CUDA-graph driver and the p-in-comm-block layout on one GPU; must reproduce
+    fea_pcg_solve bit for bit (same kernels, same order)."""
+    import ctypes
+
+    from fea_b200 import _lib
+
+    core = mods["core"]
+    lib = _lib.load()
+    nodes, elements, cons, forces = fo.cantilever_case(24, 5)
+    nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
+    K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, fixed=core._fixed_mask(cons, nodes.size))
+    b = core.to_device(forces, torch.float64).reshape(-1)
+    u_ref, info_ref = core.pcg(K, b)
+    n = K.n_dof
+    own = ctypes.c_void_p()
+    assert lib.fea_comm_alloc(lib.fea_comm_bytes(n), ctypes.byref(own)) == 0
+    handle = (ctypes.c_ubyte * 64)()
+    assert lib.fea_comm_ipc_export(own.value, ctypes.addressof(handle)) == 0 and any(handle)
+    desc = _lib.PeerComm()
+    desc.world, desc.rank, desc.lower_peer, desc.upper_peer, desc.epoch = 1, 0, -1, -1, 1
+    desc.comm[0] = own.value
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    ws = lib.fea_pcg_workspace(n)
+    work = torch.empty(ws, dtype=torch.uint8, device="cuda")
+    res = _lib.PcgResult()
+    pt = K.pattern
+    for epoch in (1, 2):  # the block is reusable across solves
+        desc.epoch = epoch
+        rc = lib.fea_pcg_solve_p2p(pt.n_nodes, 3, pt.node_rowptr.data_ptr(), pt.node_colidx.data_ptr(),
+                                   K.values.data_ptr(), pt.max_coupled, K.dinv.data_ptr(), b.data_ptr(), x.data_ptr(),
+                                   1e-12, 10 * n, work.data_ptr(), ws, ctypes.byref(desc), ctypes.byref(res), None)
+        assert rc == 0 and res.status == 0
+        assert res.iterations == info_ref.iterations
+        assert torch.equal(x, u_ref)
+    assert lib.fea_comm_free(own.value) == 0
