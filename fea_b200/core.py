@@ -143,11 +143,11 @@ class BlockCSR:
                                 _p(self.values), pt.max_coupled, _p(x), _p(y), _stream()), "fea_spmv")
         return y
 
-    def matmat(self, X: torch.Tensor) -> torch.Tensor:
+    def matmat(self, X: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """Y = K X, X (n_dof, n_rhs) row-major."""
         lib = _lib.load()
         X = X.contiguous()
-        Y = torch.empty_like(X)
+        Y = torch.empty_like(X) if out is None else out
         pt = self.pattern
         _lib.check(lib.fea_spmm(pt.n_nodes, self.dof_per_node, _p(pt.node_rowptr), _p(pt.node_colidx),
                                 _p(self.values), _p(X), _p(Y), X.shape[1], _stream()), "fea_spmm")

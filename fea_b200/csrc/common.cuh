@@ -43,6 +43,12 @@ inline int check(cudaError_t e) {
   return FEA_OK;
 }
 
+// Per-thread pinned host scratch for the solvers' state snapshots: allocated once and kept
+// (cudaMallocHost / cudaFreeHost cost 0.1-300 ms per call and cudaFreeHost synchronises the device,
+// which dominated short solves).  Returns nullptr on failure.  `slot` 0..3 are independent buffers
+// (a solver uses one; nesting solvers in one thread is not supported by the C ABI anyway).
+void* pinned_scratch(int slot, size_t bytes);
+
 #define FEA_TRY(expr)                    \
   do {                                   \
     int _rc = (expr);                    \

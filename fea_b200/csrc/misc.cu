@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "spmm.cuh"
 
 namespace fea {
 
@@ -14,54 +15,47 @@ static Profile g_profile = {0, 0, 0, 0.0, 0};
 
 Profile& profile() { return g_profile; }
 
+void* pinned_scratch(int slot, size_t bytes) {
+  struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+  };
+  thread_local Buf bufs[4];
+  if (slot < 0 || slot >= 4) return nullptr;
+  Buf& b = bufs[slot];
+  if (b.cap < bytes) {
+    if (b.p != nullptr) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = bytes < 4096 ? 4096 : bytes;
+    if (cudaMallocHost(&b.p, want) != cudaSuccess) {
+      cudaGetLastError();
+      b.p = nullptr;
+      return nullptr;
+    }
+    b.cap = want;
+  }
+  return b.p;
+}
+
 void set_last_error(cudaError_t e) {
   std::snprintf(g_err, sizeof(g_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
-// Y = K X, X/Y (n_dof, R) row-major.  Warp per node; lane <-> CPL adjacent right-hand sides of a
-// 32*CPL-wide column tile.  Matrix values are warp-uniform (broadcast) loads; X rows are read as
-// coalesced 256*CPL-byte segments.
-template <int D, int CPL>
-__global__ void __launch_bounds__(256)
+// Y = K X, X/Y (n_dof, R) row-major: G consecutive nodes per warp, see spmm.cuh.
+template <int D, int CPL, int G, int U, int MINB>
+__global__ void __launch_bounds__(32 * kSpmmWarps, MINB)
 spmm_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
             const double* __restrict__ values, const double* __restrict__ X, double* __restrict__ Y, int R) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SpmmGroupSmem<D, G>& sm = reinterpret_cast<SpmmGroupSmem<D, G>*>(s_dyn)[warp];
   const int tiles = (R + 32 * CPL - 1) / (32 * CPL);
-  for (int64_t node = warp_global; node < n_nodes; node += n_warps) {
-    const int lo = node_rowptr[node];
-    const int cnt = node_rowptr[node + 1] - lo;
-    const int row_len = D * cnt;
-    const double* v = values + (int64_t)(D * D) * lo;
-    for (int tile = 0; tile < tiles; ++tile) {
-      const int col0 = tile * 32 * CPL + lane * CPL;
-      double acc[D][CPL];
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) acc[a][j] = 0.0;
-      for (int k = 0; k < cnt; ++k) {
-        const int64_t xrow = (int64_t)D * node_colidx[lo + k];
-#pragma unroll
-        for (int b = 0; b < D; ++b) {
-          double xv[CPL];
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) xv[j] = col0 + j < R ? X[(xrow + b) * R + col0 + j] : 0.0;
-#pragma unroll
-          for (int a = 0; a < D; ++a) {
-            const double m = v[a * row_len + D * k + b];
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) acc[a][j] = fma(m, xv[j], acc[a][j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-#pragma unroll
-        for (int j = 0; j < CPL; ++j)
-          if (col0 + j < R) Y[(node * D + a) * R + col0 + j] = acc[a][j];
-    }
+  double dot[1][CPL];
+  for (int tile = 0; tile < tiles; ++tile) {
+    const int col0 = tile * 32 * CPL + lane * CPL;
+    spmm_sweep<D, CPL, G, U, false>(n_nodes, node_rowptr, node_colidx, values, X, Y, R, col0, col0 < R, lane, warp, sm,
+                                    dot);
   }
 }
 
@@ -148,15 +142,32 @@ extern "C" void fea_profile_read(double* out_host) {
   out_host[3] = (double)g_profile.pcg_iterations;
 }
 
+template <int D, int CPL, int G, int U, int MINB>
+static int launch_spmm_variant(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
+                               const double* X, double* Y, int R, cudaStream_t stream) {
+  constexpr size_t smem = sizeof(SpmmGroupSmem<D, G>) * kSpmmWarps;
+  static bool configured = false;
+  if (!configured) {
+    FEA_TRY(check(cudaFuncSetAttribute(spmm_kernel<D, CPL, G, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem)));
+    configured = true;
+  }
+  const unsigned blocks = (unsigned)std::max<int64_t>(
+      1, std::min<int64_t>(ceil_div(ceil_div(n_nodes, G), kSpmmWarps), 148LL * 2 * MINB));
+  spmm_kernel<D, CPL, G, U, MINB><<<blocks, 32 * kSpmmWarps, smem, stream>>>(n_nodes, rp, ci, values, X, Y, R);
+  return check_launch();
+}
+
 template <int D>
 static int launch_spmm(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values, const double* X,
                        double* Y, int R, cudaStream_t stream) {
-  const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_nodes, 8), 148LL * 16));
-  if (R > 32)
-    spmm_kernel<D, 2><<<blocks, 256, 0, stream>>>(n_nodes, rp, ci, values, X, Y, R);
-  else
-    spmm_kernel<D, 1><<<blocks, 256, 0, stream>>>(n_nodes, rp, ci, values, X, Y, R);
-  return check_launch();
+  if (!spmm_can_vectorise(R, X, Y))
+    return launch_spmm_variant<D, 1, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, X, Y, R, stream);
+  switch (spmm_variant()) {
+    case 1: return launch_spmm_variant<D, 2, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, X, Y, R, stream);
+    case 2: return launch_spmm_variant<D, 2, 1, 3, 3>(n_nodes, rp, ci, values, X, Y, R, stream);
+    default: return launch_spmm_variant<D, 2, 2, 3, 2>(n_nodes, rp, ci, values, X, Y, R, stream);
+  }
 }
 
 extern "C" int fea_spmm(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, const int32_t* node_colidx,

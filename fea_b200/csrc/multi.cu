@@ -11,6 +11,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "spmm.cuh"
 
 namespace fea {
 
@@ -87,45 +88,68 @@ __device__ __forceinline__ void reduce_columns(const double* partials, int s, in
   }
 }
 
-// block = (32, 8): x <-> column inside a 32-wide tile, y <-> row lane.
-constexpr int kTilesMax = kMaxRhs / 32;
+// block = (32, 8): x <-> CPL adjacent columns inside a 32*CPL-wide tile, y <-> row lane.
+// CPL = 2 (even R, 16-byte aligned arrays): every access is a 16-byte vector, a warp covers one
+// 512-byte row segment per load and two rows are in flight per trip -- the vector kernels are pure
+// HBM streams (update: 4 reads + 2 writes of n*R doubles, direction: 2 reads + 1 write).
 
+// Sum over the 8 row lanes of per-thread column sums -> s_cols[s * R + col].
+template <int CPL, int NS>
+__device__ __forceinline__ void fold_columns(const double (&v)[NS][CPL], int col0, int R, double* s_cols,
+                                             double (*s_red)[8][32 * CPL + 1]) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) s_red[s][ty][tx * CPL + j] = v[s][j];
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+        if (col0 + j < R) {
+          double t = 0.0;
+          for (int y = 0; y < 8; ++y) t += s_red[s][y][tx * CPL + j];
+          s_cols[s * R + col0 + j] = t;
+        }
+  }
+  __syncthreads();
+}
+
+template <int CPL>
 __global__ void __launch_bounds__(256)
 multi_init_kernel(int64_t n, int R, const double* __restrict__ B, const double* __restrict__ dinv,
                   double* __restrict__ X, double* __restrict__ Rv, double* __restrict__ P, double tol, int max_iter,
                   MultiWork w) {
-  __shared__ double s_red[2][8][33];
+  __shared__ double s_red[2][8][32 * CPL + 1];
   __shared__ double s_cols[2 * kMaxRhs];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int tiles = (R + 31) / 32;
+  const int tiles = (R + 32 * CPL - 1) / (32 * CPL);
   for (int tile = 0; tile < tiles; ++tile) {
-    const int col = tile * 32 + tx;
-    double a = 0.0, c = 0.0;
-    if (col < R) {
+    const int col0 = tile * 32 * CPL + tx * CPL;
+    double acc[2][CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[0][j] = acc[1][j] = 0.0;
+    if (col0 < R) {
       for (int64_t i = (int64_t)blockIdx.x * 8 + ty; i < n; i += (int64_t)gridDim.x * 8) {
         const double di = dinv[i];
-        const double ri = di != 0.0 ? B[i * R + col] : 0.0;
-        const double zi = di * ri;
-        X[i * R + col] = 0.0;
-        Rv[i * R + col] = ri;
-        P[i * R + col] = zi;
-        a = fma(ri, zi, a);
-        c = fma(ri, ri, c);
+        double bi[CPL], ri[CPL], zi[CPL], zero[CPL];
+        ColVec<CPL>::load_plain(B + i * R + col0, bi);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          ri[j] = di != 0.0 ? bi[j] : 0.0;
+          zi[j] = di * ri[j];
+          zero[j] = 0.0;
+          acc[0][j] = fma(ri[j], zi[j], acc[0][j]);
+          acc[1][j] = fma(ri[j], ri[j], acc[1][j]);
+        }
+        ColVec<CPL>::store(X + i * R + col0, zero);
+        ColVec<CPL>::store(Rv + i * R + col0, ri);
+        ColVec<CPL>::store(P + i * R + col0, zi);
       }
     }
-    s_red[0][ty][tx] = a;
-    s_red[1][ty][tx] = c;
-    __syncthreads();
-    if (ty == 0 && col < R) {
-      double sa = 0.0, sc = 0.0;
-      for (int y = 0; y < 8; ++y) {
-        sa += s_red[0][y][tx];
-        sc += s_red[1][y][tx];
-      }
-      s_cols[col] = sa;
-      s_cols[R + col] = sc;
-    }
-    __syncthreads();
+    fold_columns<CPL, 2>(acc, col0, R, s_cols, s_red);
   }
   if (publish_columns(w.partials, s_cols, 2, R, &w.st->counter[3])) {
     reduce_columns(w.partials, 0, R, w.rz);
@@ -157,82 +181,27 @@ multi_init_kernel(int64_t n, int R, const double* __restrict__ B, const double* 
   }
 }
 
-// step 1: warp per node, lane <-> CPL adjacent columns of each 32*CPL-wide tile.
-template <int D, int CPL>
-__global__ void __launch_bounds__(256)
+// step 1: AP = K P, G consecutive nodes per warp (spmm.cuh), fused with the per-column partial p.ap.
+template <int D, int CPL, int G, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 multi_spmm_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                   const double* __restrict__ values, const double* __restrict__ P, double* __restrict__ AP, int R,
                   MultiWork w) {
-  constexpr int TILES = kMaxRhs / (32 * CPL);
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ double s_cols[kMaxRhs];
-  __shared__ double s_warp[8][32 * CPL + 1];
+  __shared__ double s_red[1][8][32 * CPL + 1];
   if (w.st->done) return;
   const int lane = threadIdx.x, warp = threadIdx.y;
+  SpmmGroupSmem<D, G>& sm = reinterpret_cast<SpmmGroupSmem<D, G>*>(s_dyn)[warp];
   const int tiles = (R + 32 * CPL - 1) / (32 * CPL);
-  double dot[TILES][CPL];
+  for (int tile = 0; tile < tiles; ++tile) {
+    const int col0 = tile * 32 * CPL + lane * CPL;
+    double dot[1][CPL];
 #pragma unroll
-  for (int t = 0; t < TILES; ++t)
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) dot[t][j] = 0.0;
-  for (int64_t node = (int64_t)blockIdx.x * 8 + warp; node < n_nodes; node += (int64_t)gridDim.x * 8) {
-    const int lo = node_rowptr[node];
-    const int cnt = node_rowptr[node + 1] - lo;
-    const int row_len = D * cnt;
-    const double* v = values + (int64_t)(D * D) * lo;
-#pragma unroll
-    for (int tile = 0; tile < TILES; ++tile) {
-      if (tile < tiles) {
-        const int col0 = tile * 32 * CPL + lane * CPL;
-        double acc[D][CPL];
-#pragma unroll
-        for (int a = 0; a < D; ++a)
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) acc[a][j] = 0.0;
-        for (int k = 0; k < cnt; ++k) {
-          const int64_t xrow = (int64_t)D * node_colidx[lo + k];
-#pragma unroll
-          for (int b = 0; b < D; ++b) {
-            double xv[CPL];
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) xv[j] = col0 + j < R ? P[(xrow + b) * R + col0 + j] : 0.0;
-#pragma unroll
-            for (int a = 0; a < D; ++a) {
-              const double m = v[a * row_len + D * k + b];
-#pragma unroll
-              for (int j = 0; j < CPL; ++j) acc[a][j] = fma(m, xv[j], acc[a][j]);
-            }
-          }
-        }
-#pragma unroll
-        for (int a = 0; a < D; ++a)
-#pragma unroll
-          for (int j = 0; j < CPL; ++j)
-            if (col0 + j < R) {
-              const int64_t idx = (node * D + a) * R + col0 + j;
-              AP[idx] = acc[a][j];
-              dot[tile][j] = fma(acc[a][j], P[idx], dot[tile][j]);
-            }
-      }
-    }
-  }
-  // block reduction of the per-column dots, tile by tile
-#pragma unroll
-  for (int tile = 0; tile < TILES; ++tile) {
-    if (tile < tiles) {
-#pragma unroll
-      for (int j = 0; j < CPL; ++j) s_warp[warp][lane * CPL + j] = dot[tile][j];
-      __syncthreads();
-      if (warp == 0) {
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          const int col = tile * 32 * CPL + lane * CPL + j;
-          double t = 0.0;
-          for (int y = 0; y < 8; ++y) t += s_warp[y][lane * CPL + j];
-          if (col < R) s_cols[col] = t;
-        }
-      }
-      __syncthreads();
-    }
+    for (int j = 0; j < CPL; ++j) dot[0][j] = 0.0;
+    spmm_sweep<D, CPL, G, U, true>(n_nodes, node_rowptr, node_colidx, values, P, AP, R, col0, col0 < R, lane, warp, sm,
+                                   dot);
+    fold_columns<CPL, 1>(dot, col0, R, s_cols, s_red);
   }
   if (publish_columns(w.partials, s_cols, 1, R, &w.st->counter[0])) {
     reduce_columns(w.partials, 0, R, w.pap);
@@ -242,10 +211,11 @@ multi_spmm_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, cons
 }
 
 // step 2
+template <int CPL>
 __global__ void __launch_bounds__(256)
 multi_update_kernel(int64_t n, int R, const double* __restrict__ dinv, const double* __restrict__ P,
                     const double* __restrict__ AP, double* __restrict__ X, double* __restrict__ Rv, MultiWork w) {
-  __shared__ double s_red[2][8][33];
+  __shared__ double s_red[2][8][32 * CPL + 1];
   __shared__ double s_cols[2 * kMaxRhs];
   __shared__ int s_bad;
   MultiState* st = w.st;
@@ -253,41 +223,65 @@ multi_update_kernel(int64_t n, int R, const double* __restrict__ dinv, const dou
   const int tx = threadIdx.x, ty = threadIdx.y;
   if (tx == 0 && ty == 0) s_bad = 0;
   __syncthreads();
-  const int tiles = (R + 31) / 32;
+  const int tiles = (R + 32 * CPL - 1) / (32 * CPL);
+  const int64_t step = (int64_t)gridDim.x * 8;
   for (int tile = 0; tile < tiles; ++tile) {
-    const int col = tile * 32 + tx;
-    double a = 0.0, c = 0.0;
-    if (col < R) {
-      double alpha = 0.0;
-      if (w.active[col]) {
-        const double pap = w.pap[col];
-        if (pap > 0.0) alpha = w.rz[col] / pap; else s_bad = 1;
-      }
-      for (int64_t i = (int64_t)blockIdx.x * 8 + ty; i < n; i += (int64_t)gridDim.x * 8) {
-        const int64_t idx = i * R + col;
-        const double di = dinv[i];
-        const double ri = fma(-alpha, AP[idx], Rv[idx]);
-        X[idx] = fma(alpha, P[idx], X[idx]);
-        Rv[idx] = ri;
-        if (di != 0.0) {
-          a = fma(ri * di, ri, a);
-          c = fma(ri, ri, c);
+    const int col0 = tile * 32 * CPL + tx * CPL;
+    double acc[2][CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[0][j] = acc[1][j] = 0.0;
+    if (col0 < R) {
+      double alpha[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        alpha[j] = 0.0;
+        if (col0 + j < R && w.active[col0 + j]) {
+          const double pap = w.pap[col0 + j];
+          if (pap > 0.0) alpha[j] = w.rz[col0 + j] / pap; else s_bad = 1;
         }
       }
-    }
-    s_red[0][ty][tx] = a;
-    s_red[1][ty][tx] = c;
-    __syncthreads();
-    if (ty == 0 && col < R) {
-      double sa = 0.0, sc = 0.0;
-      for (int y = 0; y < 8; ++y) {
-        sa += s_red[0][y][tx];
-        sc += s_red[1][y][tx];
+      auto finish = [&](int64_t idx, double di, const double (&ap)[CPL], double (&rv)[CPL], const double (&pv)[CPL],
+                        double (&xv)[CPL]) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          rv[j] = fma(-alpha[j], ap[j], rv[j]);
+          xv[j] = fma(alpha[j], pv[j], xv[j]);
+          if (di != 0.0) {
+            acc[0][j] = fma(rv[j] * di, rv[j], acc[0][j]);
+            acc[1][j] = fma(rv[j], rv[j], acc[1][j]);
+          }
+        }
+        ColVec<CPL>::store(X + idx, xv);
+        ColVec<CPL>::store(Rv + idx, rv);
+      };
+      int64_t i = (int64_t)blockIdx.x * 8 + ty;
+      for (; i + step < n; i += 2 * step) {  // two rows in flight: 8 independent vector loads per thread
+        const int64_t i0 = i * R + col0, i1 = (i + step) * R + col0;
+        double ap0[CPL], rv0[CPL], pv0[CPL], xv0[CPL], ap1[CPL], rv1[CPL], pv1[CPL], xv1[CPL];
+        const double d0 = dinv[i], d1 = dinv[i + step];
+        ColVec<CPL>::load_plain(AP + i0, ap0);
+        ColVec<CPL>::load_plain(Rv + i0, rv0);
+        ColVec<CPL>::load_plain(P + i0, pv0);
+        ColVec<CPL>::load_plain(X + i0, xv0);
+        ColVec<CPL>::load_plain(AP + i1, ap1);
+        ColVec<CPL>::load_plain(Rv + i1, rv1);
+        ColVec<CPL>::load_plain(P + i1, pv1);
+        ColVec<CPL>::load_plain(X + i1, xv1);
+        finish(i0, d0, ap0, rv0, pv0, xv0);
+        finish(i1, d1, ap1, rv1, pv1, xv1);
       }
-      s_cols[col] = sa;
-      s_cols[R + col] = sc;
+      for (; i < n; i += step) {
+        const int64_t i0 = i * R + col0;
+        double ap0[CPL], rv0[CPL], pv0[CPL], xv0[CPL];
+        const double d0 = dinv[i];
+        ColVec<CPL>::load_plain(AP + i0, ap0);
+        ColVec<CPL>::load_plain(Rv + i0, rv0);
+        ColVec<CPL>::load_plain(P + i0, pv0);
+        ColVec<CPL>::load_plain(X + i0, xv0);
+        finish(i0, d0, ap0, rv0, pv0, xv0);
+      }
     }
-    __syncthreads();
+    fold_columns<CPL, 2>(acc, col0, R, s_cols, s_red);
   }
   const bool bad = s_bad != 0;
   if (publish_columns(w.partials, s_cols, 2, R, &st->counter[1])) {
@@ -306,6 +300,7 @@ multi_update_kernel(int64_t n, int R, const double* __restrict__ dinv, const dou
 }
 
 // step 3
+template <int CPL>
 __global__ void __launch_bounds__(256)
 multi_direction_kernel(int64_t n, int R, const double* __restrict__ dinv, const double* __restrict__ Rv,
                        double* __restrict__ P, MultiWork w) {
@@ -313,16 +308,45 @@ multi_direction_kernel(int64_t n, int R, const double* __restrict__ dinv, const 
   MultiState* st = w.st;
   if (st->done) return;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int tiles = (R + 31) / 32;
+  const int tiles = (R + 32 * CPL - 1) / (32 * CPL);
   const double tol2 = st->tol2;
+  const int64_t step = (int64_t)gridDim.x * 8;
   for (int tile = 0; tile < tiles; ++tile) {
-    const int col = tile * 32 + tx;
-    if (col < R) {
-      double beta = 0.0;
-      if (w.active[col] && !(w.rr[col] <= tol2 * w.bnorm2[col])) beta = w.rz_new[col] / w.rz[col];
-      for (int64_t i = (int64_t)blockIdx.x * 8 + ty; i < n; i += (int64_t)gridDim.x * 8) {
-        const int64_t idx = i * R + col;
-        P[idx] = fma(beta, P[idx], dinv[i] * Rv[idx]);
+    const int col0 = tile * 32 * CPL + tx * CPL;
+    if (col0 < R) {
+      double beta[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int col = col0 + j;
+        beta[j] = 0.0;
+        if (col < R && w.active[col] && !(w.rr[col] <= tol2 * w.bnorm2[col])) beta[j] = w.rz_new[col] / w.rz[col];
+      }
+      int64_t i = (int64_t)blockIdx.x * 8 + ty;
+      for (; i + 3 * step < n; i += 4 * step) {  // four rows in flight
+        double rv[4][CPL], pv[4][CPL], di[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t idx = (i + u * step) * R + col0;
+          di[u] = dinv[i + u * step];
+          ColVec<CPL>::load_plain(Rv + idx, rv[u]);
+          ColVec<CPL>::load_plain(P + idx, pv[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) pv[u][j] = fma(beta[j], pv[u][j], di[u] * rv[u][j]);
+          ColVec<CPL>::store(P + (i + u * step) * R + col0, pv[u]);
+        }
+      }
+      for (; i < n; i += step) {
+        const int64_t idx = i * R + col0;
+        const double di = dinv[i];
+        double rv[CPL], pv[CPL];
+        ColVec<CPL>::load_plain(Rv + idx, rv);
+        ColVec<CPL>::load_plain(P + idx, pv);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) pv[j] = fma(beta[j], pv[j], di * rv[j]);
+        ColVec<CPL>::store(P + idx, pv);
       }
     }
   }
@@ -359,15 +383,31 @@ multi_direction_kernel(int64_t n, int R, const double* __restrict__ dinv, const 
   }
 }
 
+template <int D, int CPL, int G, int U, int MINB>
+static int launch_multi_spmm_variant(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
+                                     const double* P, double* AP, int R, const MultiWork& w, cudaStream_t stream) {
+  constexpr size_t smem = sizeof(SpmmGroupSmem<D, G>) * kSpmmWarps;
+  static bool configured = false;
+  if (!configured) {
+    FEA_TRY(check(cudaFuncSetAttribute(multi_spmm_kernel<D, CPL, G, U, MINB>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    configured = true;
+  }
+  const unsigned blocks = (unsigned)std::max<int64_t>(
+      1, std::min<int64_t>(ceil_div(ceil_div(n_nodes, G), kSpmmWarps), std::min(148 * 2 * MINB, kMultiBlocks)));
+  multi_spmm_kernel<D, CPL, G, U, MINB><<<blocks, dim3(32, 8), smem, stream>>>(n_nodes, rp, ci, values, P, AP, R, w);
+  return FEA_OK;
+}
+
 template <int D>
-static void launch_multi_spmm(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
-                              const double* P, double* AP, int R, const MultiWork& w, unsigned blocks,
-                              cudaStream_t stream) {
-  dim3 block(32, 8);
-  if (R > 32)
-    multi_spmm_kernel<D, 2><<<blocks, block, 0, stream>>>(n_nodes, rp, ci, values, P, AP, R, w);
-  else
-    multi_spmm_kernel<D, 1><<<blocks, block, 0, stream>>>(n_nodes, rp, ci, values, P, AP, R, w);
+static int launch_multi_spmm(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
+                             const double* P, double* AP, int R, bool vec, const MultiWork& w, cudaStream_t stream) {
+  if (!vec) return launch_multi_spmm_variant<D, 1, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream);
+  switch (spmm_variant()) {
+    case 1: return launch_multi_spmm_variant<D, 2, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream);
+    case 2: return launch_multi_spmm_variant<D, 2, 1, 3, 3>(n_nodes, rp, ci, values, P, AP, R, w, stream);
+    default: return launch_multi_spmm_variant<D, 2, 2, 3, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream);
+  }
 }
 
 }  // namespace fea
@@ -389,26 +429,26 @@ extern "C" int fea_pcg_solve_multi(int64_t n_nodes, int32_t d, const int32_t* no
   if (work_bytes < multi_bytes(n, R)) return FEA_ERR_WORKSPACE;
   MultiWork w = carve_multi(work, n, R);
 
-  MultiState* snap = nullptr;
-  FEA_TRY(check(cudaMallocHost(&snap, 2 * sizeof(MultiState))));
+  MultiState* snap = static_cast<MultiState*>(pinned_scratch(0, 2 * sizeof(MultiState)));
+  if (snap == nullptr) return FEA_ERR_CUDA;
   cudaEvent_t ev[2];
   int rc = check(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  if (rc != FEA_OK) {
-    cudaFreeHost(snap);
-    return rc;
-  }
+  if (rc != FEA_OK) return rc;
   rc = check(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
   if (rc != FEA_OK) {
     cudaEventDestroy(ev[0]);
-    cudaFreeHost(snap);
     return rc;
   }
   const unsigned vb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 8 * 8), kMultiBlocks));
-  const unsigned sb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_nodes, 8), kMultiBlocks));
   const dim3 block(32, 8);
+  // 16-byte vector path: even R and aligned caller arrays (the workspace vectors are 256 B aligned)
+  const bool vec = spmm_can_vectorise(R, B, X);
   rc = check(cudaMemsetAsync(w.st, 0, 256, stream));
   if (rc == FEA_OK) {
-    multi_init_kernel<<<vb, block, 0, stream>>>(n, R, B, dinv, X, w.Rv, w.P, tol, max_iter, w);
+    if (vec)
+      multi_init_kernel<2><<<vb, block, 0, stream>>>(n, R, B, dinv, X, w.Rv, w.P, tol, max_iter, w);
+    else
+      multi_init_kernel<1><<<vb, block, 0, stream>>>(n, R, B, dinv, X, w.Rv, w.P, tol, max_iter, w);
     rc = check_launch();
   }
   const int chunk = 16;
@@ -419,14 +459,20 @@ extern "C" int fea_pcg_solve_multi(int64_t n_nodes, int32_t d, const int32_t* no
     const int todo = std::min(chunk, max_iter - enqueued);
     for (int it = 0; it < todo; ++it) {
       switch (d) {
-        case 1: launch_multi_spmm<1>(n_nodes, node_rowptr, node_colidx, values, w.P, w.AP, R, w, sb, stream); break;
-        case 2: launch_multi_spmm<2>(n_nodes, node_rowptr, node_colidx, values, w.P, w.AP, R, w, sb, stream); break;
-        default: launch_multi_spmm<3>(n_nodes, node_rowptr, node_colidx, values, w.P, w.AP, R, w, sb, stream); break;
+        case 1: rc = launch_multi_spmm<1>(n_nodes, node_rowptr, node_colidx, values, w.P, w.AP, R, vec, w, stream); break;
+        case 2: rc = launch_multi_spmm<2>(n_nodes, node_rowptr, node_colidx, values, w.P, w.AP, R, vec, w, stream); break;
+        default: rc = launch_multi_spmm<3>(n_nodes, node_rowptr, node_colidx, values, w.P, w.AP, R, vec, w, stream); break;
       }
-      multi_update_kernel<<<vb, block, 0, stream>>>(n, R, dinv, w.P, w.AP, X, w.Rv, w);
-      multi_direction_kernel<<<vb, block, 0, stream>>>(n, R, dinv, w.Rv, w.P, w);
+      if (rc != FEA_OK) break;
+      if (vec) {
+        multi_update_kernel<2><<<vb, block, 0, stream>>>(n, R, dinv, w.P, w.AP, X, w.Rv, w);
+        multi_direction_kernel<2><<<vb, block, 0, stream>>>(n, R, dinv, w.Rv, w.P, w);
+      } else {
+        multi_update_kernel<1><<<vb, block, 0, stream>>>(n, R, dinv, w.P, w.AP, X, w.Rv, w);
+        multi_direction_kernel<1><<<vb, block, 0, stream>>>(n, R, dinv, w.Rv, w.P, w);
+      }
     }
-    rc = check_launch(3 * todo);
+    if (rc == FEA_OK) rc = check_launch(3 * todo);
     if (rc != FEA_OK) break;
     enqueued += todo;
     rc = check(cudaMemcpyAsync(&snap[slot], w.st, sizeof(MultiState), cudaMemcpyDeviceToHost, stream));
@@ -448,8 +494,8 @@ extern "C" int fea_pcg_solve_multi(int64_t n_nodes, int32_t d, const int32_t* no
     rc = check(cudaMemcpyAsync(&snap[0], w.st, sizeof(MultiState), cudaMemcpyDeviceToHost, stream));
     if (rc == FEA_OK && iterations_host != nullptr)
       rc = check(cudaMemcpyAsync(iterations_host, w.iters, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, stream));
-    double* cols = nullptr;
-    if (rc == FEA_OK) rc = check(cudaMallocHost(&cols, sizeof(double) * 2 * R));
+    double* cols = static_cast<double*>(pinned_scratch(1, sizeof(double) * 2 * R));
+    if (rc == FEA_OK && cols == nullptr) rc = FEA_ERR_CUDA;
     if (rc == FEA_OK) {
       rc = check(cudaMemcpyAsync(cols, w.bnorm2, sizeof(double) * R, cudaMemcpyDeviceToHost, stream));
       if (rc == FEA_OK) rc = check(cudaMemcpyAsync(cols + R, w.rr, sizeof(double) * R, cudaMemcpyDeviceToHost, stream));
@@ -460,7 +506,6 @@ extern "C" int fea_pcg_solve_multi(int64_t n_nodes, int32_t d, const int32_t* no
           bn = std::max(bn, std::sqrt(cols[j]));
         }
       }
-      cudaFreeHost(cols);
     }
   }
   if (rc == FEA_OK) {
@@ -474,6 +519,5 @@ extern "C" int fea_pcg_solve_multi(int64_t n_nodes, int32_t d, const int32_t* no
   }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
-  cudaFreeHost(snap);
   return rc;
 }

@@ -252,8 +252,8 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   }
   const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_owned_nodes);
 
-  PcgState* snap = nullptr;
-  FEA_TRY(check(cudaMallocHost(&snap, 2 * sizeof(PcgState))));
+  PcgState* snap = static_cast<PcgState*>(pinned_scratch(0, 2 * sizeof(PcgState)));
+  if (snap == nullptr) return FEA_ERR_CUDA;
   cudaEvent_t ev[2] = {nullptr, nullptr}, ev_order = nullptr;
   cudaStream_t stream = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -360,6 +360,5 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   }
   for (cudaEvent_t e : {ev[0], ev[1], ev_order})
     if (e != nullptr) cudaEventDestroy(e);
-  cudaFreeHost(snap);
   return rc;
 }

@@ -547,17 +547,13 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_nodes);
 
   // two pinned snapshots of the state, polled one chunk behind the GPU
-  PcgState* snap = nullptr;
-  FEA_TRY(check(cudaMallocHost(&snap, 2 * sizeof(PcgState))));
+  PcgState* snap = static_cast<PcgState*>(pinned_scratch(0, 2 * sizeof(PcgState)));
+  if (snap == nullptr) return FEA_ERR_CUDA;
   cudaEvent_t ev[2];
   int rc = FEA_OK;
-  if ((rc = check(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming))) != FEA_OK) {
-    cudaFreeHost(snap);
-    return rc;
-  }
+  if ((rc = check(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming))) != FEA_OK) return rc;
   if ((rc = check(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming))) != FEA_OK) {
     cudaEventDestroy(ev[0]);
-    cudaFreeHost(snap);
     return rc;
   }
 
@@ -679,7 +675,6 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   }
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
-  cudaFreeHost(snap);
   if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
   if (own != nullptr) {
     // the solve has been synchronised above; order the caller's stream after it anyway

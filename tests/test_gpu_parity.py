@@ -342,6 +342,43 @@ def test_truss_lattice_multi_rhs(mods):
     assert rel(u1.ravel(), X[:, 0]) < 1e-9
 
 
+def test_spmm_and_multi_rhs_wide_rows_and_odd_widths(mods):
+    """Hub-and-spoke truss: the hub couples to 70 nodes (> one 32-node staging round of the SpMM),
+    leaves couple to ~8.  SpMM and the batched PCG at odd, even, multi-tile RHS counts (scalar and
+    16-byte vector paths) against scipy / sparse LU."""
+    import scipy.sparse.linalg as spla
+
+    core, T = mods["core"], mods["truss"]
+    rng = np.random.default_rng(11)
+    n_leaf = 70
+    leaf = rng.standard_normal((n_leaf, 3))
+    leaf /= np.linalg.norm(leaf, axis=1)[:, None]
+    pts = np.concatenate([[[0.0, 0.0, 0.0]], leaf * (1 + 0.2 * rng.random((n_leaf, 1)))])
+    dist = np.linalg.norm(leaf[:, None] - leaf[None], axis=2)
+    np.fill_diagonal(dist, 9.0)
+    near = np.argsort(dist, axis=1)[:, :6]  # shell: every leaf to its 6 nearest leaves (cond(K_ff) ~ 8e2)
+    pairs = sorted({(min(i, j) + 1, max(i, j) + 1) for i in range(n_leaf) for j in near[i]})
+    members = np.concatenate([np.stack([np.zeros(n_leaf, dtype=np.int64), np.arange(1, n_leaf + 1)], axis=1),
+                              np.array(pairs)])
+    k = rng.uniform(500.0, 1500.0, members.shape[0])
+    cons = np.zeros((n_leaf + 1, 3), dtype=int)
+    cons[1:8] = 1
+    K = core.assemble_truss(core.to_device(pts, torch.float64), core.to_device(members, torch.int32),
+                            core.to_device(k, torch.float64), fixed=core._fixed_mask(cons, pts.size))
+    assert K.pattern.max_coupled == n_leaf + 1
+    Kref = fo.assemble_csr(members, fo.truss_ke_batched(pts, members, k), pts.shape[0], 3)
+    free = fo.free_dofs(cons)
+    lu = spla.splu(Kref[free][:, free].tocsc())
+    for r in (1, 5, 64, 130):
+        X = rng.standard_normal((K.n_dof, r))
+        Y = K.matmat(core.to_device(X, torch.float64)).cpu().numpy()
+        assert rel(Y, Kref @ X) < 1e-13
+        U, info = core.pcg_multi(K, core.to_device(X, torch.float64), tol=1e-12)
+        U = U.cpu().numpy()
+        assert info.status == 0 and info.rel_residual <= 1e-12
+        assert rel(U[free], lu.solve(X[free])) < U_RTOL
+
+
 def test_mesh_extrude_device(mods):
     U, C = mods["utils"], mods["cubebeam"]
     n2, q2 = C.generate_quad_grid(5, 3, 0.3, 0.2)
