@@ -40,6 +40,7 @@ __device__ __forceinline__ double eliminate(double v, const uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------
 constexpr int kAsmWarps = 4;
 
+template <bool FACTORED>
 __global__ void __launch_bounds__(kAsmWarps * 32)
 assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ elements, int64_t n_nodes,
                      Hex8Material mat, const int32_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e,
@@ -90,7 +91,7 @@ assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict
       int slot = 0;
       if (active) {  // phase B
         const int b = lane & 7;
-        hex8_block(grad, detj, t, a_own, b, mat, blk);
+        hex8_block<FACTORED>(grad, detj, t, a_own, b, mat, blk);
         slot = find_slot(cols, cnt, elements[(int64_t)e * 8 + b]);
       }
       // phase C: element order; inside one element the 8 column nodes are distinct
@@ -324,12 +325,22 @@ extern "C" int fea_assemble_hex8(const double* nodes, const int32_t* elements, i
   const int per_warp = kGradDoubles + 32 + 9 * maxc + (maxc + 1) / 2;
   const size_t smem = sizeof(double) * (kShapeTable + (size_t)kAsmWarps * per_warp);
   if (smem > 200 * 1024) return FEA_ERR_INVALID;  // valence too high for the on-chip accumulator
-  if (smem > 48 * 1024)
-    FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  const bool legacy = hex8_legacy_block();
+  if (smem > 48 * 1024) {
+    FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem)));
+    FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem)));
+  }
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, kAsmWarps), 148LL * 64);
-  assemble_hex8_kernel<<<blocks, kAsmWarps * 32, smem, stream>>>(nodes, elements, n_nodes, hex8_material(E, nu),
-                                                                 n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed,
-                                                                 mode, values, dinv, status);
+  if (legacy)
+    assemble_hex8_kernel<false><<<blocks, kAsmWarps * 32, smem, stream>>>(
+        nodes, elements, n_nodes, hex8_material(E, nu), n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed, mode,
+        values, dinv, status);
+  else
+    assemble_hex8_kernel<true><<<blocks, kAsmWarps * 32, smem, stream>>>(
+        nodes, elements, n_nodes, hex8_material(E, nu), n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed, mode,
+        values, dinv, status);
   return check_launch();
 }
 

@@ -14,6 +14,7 @@ namespace fea {
 //   phase B: lane = (t, b): the eight 3x3 blocks K_ab, a = 0..7, written to ke[e][3a+r][3b+c].
 constexpr int kKeWarps = 4;
 
+template <bool FACTORED>
 __global__ void __launch_bounds__(kKeWarps * 32) ke_hex8_kernel(const double* __restrict__ nodes,
                                                                 const int32_t* __restrict__ elements,
                                                                 int64_t n_elem, Hex8Material mat,
@@ -21,11 +22,13 @@ __global__ void __launch_bounds__(kKeWarps * 32) ke_hex8_kernel(const double* __
   __shared__ double s_tab[kShapeTable];
   __shared__ double s_grad[kKeWarps][kGradDoubles];
   __shared__ double s_detj[kKeWarps][32];
+  __shared__ double s_stage[kKeWarps][4 * 72];
   hex8_fill_shape_table(s_tab);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* grad = s_grad[warp];
   double* detj = s_detj[warp];
+  double* stage = s_stage[warp];
   const int64_t n_groups = (n_elem + 3) / 4;
   for (int64_t g = (int64_t)blockIdx.x * kKeWarps + warp; g < n_groups; g += (int64_t)gridDim.x * kKeWarps) {
     {  // phase A
@@ -38,20 +41,29 @@ __global__ void __launch_bounds__(kKeWarps * 32) ke_hex8_kernel(const double* __
       }
     }
     __syncwarp();
-    {  // phase B
+    {  // phase B: block row a of the 4 elements = 3 full rows of each Ke = 72 contiguous doubles per
+       // element; staged through shared memory so that every store instruction of the warp writes
+       // 256 contiguous bytes (direct stores touched 24 sectors per 256 B of payload).
       const int t = lane >> 3, b = lane & 7;
       const int64_t e = g * 4 + t;
-      if (e < n_elem) {
-        double* out = ke + e * 576;
+      const int64_t e0 = g * 4;
+      const int n_here = (int)min((int64_t)4, n_elem - e0);
 #pragma unroll 1
-        for (int a = 0; a < 8; ++a) {
+      for (int a = 0; a < 8; ++a) {
+        if (e < n_elem) {
           double blk[3][3];
-          hex8_block(grad, detj, t, a, b, mat, blk);
+          hex8_block<FACTORED>(grad, detj, t, a, b, mat, blk);
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) out[(3 * a + r) * 24 + 3 * b + c] = blk[r][c];
+            for (int c = 0; c < 3; ++c) stage[t * 72 + r * 24 + 3 * b + c] = blk[r][c];
         }
+        __syncwarp();
+        for (int q = lane; q < 72 * n_here; q += 32) {
+          const int tt = q / 72, w = q - tt * 72;
+          __stcs(ke + (e0 + tt) * 576 + a * 72 + w, stage[q]);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -109,7 +121,12 @@ extern "C" int fea_ke_hex8(const double* nodes, const int32_t* elements, int64_t
   if (n_elem == 0) return FEA_OK;
   const int64_t groups = ceil_div(n_elem, 4);
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(groups, kKeWarps), 148LL * 16);
-  ke_hex8_kernel<<<blocks, kKeWarps * 32, 0, stream>>>(nodes, elements, n_elem, hex8_material(E, nu), ke, status);
+  if (hex8_legacy_block())
+    ke_hex8_kernel<false><<<blocks, kKeWarps * 32, 0, stream>>>(nodes, elements, n_elem, hex8_material(E, nu), ke,
+                                                                  status);
+  else
+    ke_hex8_kernel<true><<<blocks, kKeWarps * 32, 0, stream>>>(nodes, elements, n_elem, hex8_material(E, nu), ke,
+                                                                 status);
   return check_launch();
 }
 

@@ -4,21 +4,21 @@
 // p with the two z-neighbours (157 KB each at 400x80x80) and two tiny all-reduces.  Through NCCL
 // that is three collectives of ~15-20 us each per iteration, issued by the host; at 8 ranks a rank's
 // kernels only take ~0.13 ms per iteration, so latency dominates.  Here every rank maps its peers'
-// communication blocks (CUDA IPC, NVSwitch gives every pair full bandwidth) and the exchange is
-// done by three tiny kernels per iteration that live in the same stream / CUDA graph as the
-// solver kernels:
+// communication blocks (CUDA IPC, NVSwitch gives every pair full bandwidth) and the exchange
+// happens INSIDE the three solver kernels of an iteration (pcg.cu, primitives in pcg_common.cuh),
+// which stay the only launches of the CUDA graph:
 //
-//   p2p_halo_kernel       push my boundary layer of p straight into the neighbours' halo rows
-//                         (coalesced remote stores), release-store an iteration tag into their
-//                         header, then wait for the neighbours' tags           (~6 us)
-//   p2p_allreduce_kernel  one warp: lane r stores this rank's partial sum(s) + tag into rank r's
-//                         slot array, then waits for rank r's slot in the own array; lane 0 adds the
-//                         world values in rank order -- every rank gets the bitwise identical sum,
-//                         deterministic, no atomics                           (~4 us)
+//   SpMV       last block: publish this rank's p.Ap to every rank's slot array (one warp, NVLink stores)
+//   update     every CTA: collect the world's p.Ap from the own slot array (local L2 polls), add
+//              in rank order -> alpha; last block: publish (r.z, r.r)
+//   direction  every CTA: collect (r.z, r.r) -> beta / convergence; the boundary rows of the new p
+//              are stored straight into the neighbours' halo rows while p is written; last block:
+//              release the iteration tag to the neighbours and wait for theirs
 //
-// Tags are (epoch << 32 | iteration + 1), slots are double-buffered by iteration parity; a rank can
-// never be two exchanges ahead of a peer because every exchange needs every rank's contribution.
-// Spins are bounded: a peer that never arrives raises FEA_ERR_PEER instead of hanging the GPU.
+// The first version used three extra single-purpose kernels per iteration (halo push, two
+// all-reduces: 6 launches instead of 3); they remain for the one exchange after the init kernel.
+// Every rank forms bitwise identical sums (rank order, no atomics), hence identical convergence
+// decisions.  Spins are bounded: a peer that never arrives raises FEA_ERR_PEER instead of hanging.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -28,70 +28,12 @@
 
 namespace fea {
 
-constexpr int kMaxPeers = FEA_MAX_PEERS;
-constexpr size_t kCommHeaderBytes = 4096;
-
-struct PeerSlot {
-  double v[2];
-  long long tag;
-  long long pad;
-};
-struct CommHeader {
-  PeerSlot slots[2][3][kMaxPeers];  // [parity][kind][source rank]
-  long long halo_tag[2];            // [0] written by the lower neighbour, [1] by the upper one
-  unsigned int counter;             // last-block ticket of the halo kernel
-  int error;
-};
-static_assert(sizeof(CommHeader) <= kCommHeaderBytes, "comm header");
-
-struct PeerView {  // kernel argument
-  int world, rank, lower, upper;
-  CommHeader* hdr[kMaxPeers];
-  double* lower_dst;
-  double* upper_dst;
-  const double* lower_src;
-  const double* upper_src;
-  long long lower_cnt, upper_cnt;
-  long long epoch;
-};
-
-__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
-  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
-  long long v;
-  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ld_volatile_f64(const double* p) {
-  double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-// Bounded spin (about 2 s): true when *p reaches `want` (exactly, or at least with `at_least`).
-__device__ __forceinline__ bool spin_until(const long long* p, long long want, bool at_least) {
-  for (int i = 0; i < (1 << 24); ++i) {
-    const long long v = ld_acquire_sys(p);
-    if (at_least ? v >= want : v == want) return true;
-    __nanosleep(100);
-  }
-  return false;
-}
-__device__ __forceinline__ void peer_failure(const PeerView& pv, PcgState* st) {
-  pv.hdr[pv.rank]->error = 1;
-  st->status = FEA_ERR_PEER;
-  st->done = 1;
-  st->rr_final = st->rr;
-}
-
 // kind 0: (rz, bnorm2) after init; kind 1: pap after step 1; kind 2: (rz_new, rr) after step 2.
 __global__ void __launch_bounds__(32) p2p_allreduce_kernel(PeerView pv, PcgState* st, int kind) {
   if (st->done) return;
   const int lane = threadIdx.x;
   // iteration this exchange belongs to: step 2 has already incremented st->iter
   const long long k = kind == 2 ? st->iter - 1 : st->iter;
-  const long long tag = (pv.epoch << 32) | (k + 1);
-  const int parity = (int)(k & 1);
   double mine0, mine1;
   if (kind == 0) {
     mine0 = st->rz;
@@ -103,27 +45,9 @@ __global__ void __launch_bounds__(32) p2p_allreduce_kernel(PeerView pv, PcgState
     mine0 = st->rz_new;
     mine1 = st->rr;
   }
-  if (lane < pv.world) {
-    PeerSlot* dst = &pv.hdr[lane]->slots[parity][kind][pv.rank];
-    dst->v[0] = mine0;
-    dst->v[1] = mine1;
-    __threadfence_system();
-    st_release_sys(&dst->tag, tag);
-  }
-  double v0 = 0.0, v1 = 0.0;
-  bool ok = true;
-  if (lane < pv.world) {
-    const PeerSlot* src = &pv.hdr[pv.rank]->slots[parity][kind][lane];
-    ok = spin_until(&src->tag, tag, false);
-    v0 = ld_volatile_f64(&src->v[0]);
-    v1 = ld_volatile_f64(&src->v[1]);
-  }
-  const bool all_ok = __all_sync(kFull, ok);
-  double s0 = 0.0, s1 = 0.0;
-  for (int r = 0; r < pv.world; ++r) {  // rank order: identical sums on every rank
-    s0 += __shfl_sync(kFull, v0, r);
-    s1 += __shfl_sync(kFull, v1, r);
-  }
+  peer_publish(pv, kind, k, mine0, mine1);
+  double s0, s1;
+  const bool all_ok = peer_collect(pv, kind, k, s0, s1);
   if (lane == 0) {
     if (!all_ok) {
       peer_failure(pv, st);
@@ -143,7 +67,7 @@ __global__ void __launch_bounds__(32) p2p_allreduce_kernel(PeerView pv, PcgState
 __global__ void __launch_bounds__(256) p2p_halo_kernel(PeerView pv, PcgState* st) {
   __shared__ bool s_last;
   if (st->done) return;
-  const long long tag = (pv.epoch << 32) | ((long long)st->iter + 1);
+  const long long tag = peer_tag(pv, st->iter);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pv.lower >= 0)
@@ -241,15 +165,20 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   double* p_ext = p_ext_of(comm->rank);
   double* p_own = p_ext + comm->own_offset_nodes * d;
   if (pv.lower >= 0) {
-    pv.lower_src = p_own + comm->send_lower_first * d;
+    pv.lower_off = comm->send_lower_first * d;
+    pv.lower_src = p_own + pv.lower_off;
     pv.lower_cnt = comm->send_lower_count * d;
     pv.lower_dst = p_ext_of(pv.lower) + comm->send_lower_dst * d;
   }
   if (pv.upper >= 0) {
-    pv.upper_src = p_own + comm->send_upper_first * d;
+    pv.upper_off = comm->send_upper_first * d;
+    pv.upper_src = p_own + pv.upper_off;
     pv.upper_cnt = comm->send_upper_count * d;
     pv.upper_dst = p_ext_of(pv.upper) + comm->send_upper_dst * d;
   }
+  // device copy of the view inside this rank's own header page (peers only write the slot arrays)
+  const PeerView* pv_dev =
+      reinterpret_cast<const PeerView*>(static_cast<char*>(comm->comm[comm->rank]) + kCommViewOffset);
   const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_owned_nodes);
 
   PcgState* snap = static_cast<PcgState*>(pinned_scratch(0, 2 * sizeof(PcgState)));
@@ -273,22 +202,22 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   auto halo = [&]() {
     if (multi) p2p_halo_kernel<<<halo_blocks, 256, 0, stream>>>(pv, state);
   };
+  const PeerView* pv_it = multi ? pv_dev : nullptr;
   auto iteration = [&]() -> int {
     const int r1 = pcg_step_spmv(d, n_owned_nodes, node_rowptr_owned, node_colidx, values, p_ext, ap,
-                                 comm->own_offset_nodes, state, partials, stream, &plan);
-    exchange(1);
-    pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials);
-    exchange(2);
-    pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, nullptr);
-    halo();
+                                 comm->own_offset_nodes, state, partials, stream, &plan, pv_it);
+    pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials, pv_it);
+    pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, nullptr, pv_it);
     return r1;
   };
-  const int launches_per_iteration = multi ? 6 : 3;
+  const int launches_per_iteration = 3;
 
   if (rc == FEA_OK) {
     pcg_match_carveout();
     rc = check(cudaMemsetAsync(state, 0, FEA_PCG_STATE_BYTES, stream));
   }
+  if (rc == FEA_OK)
+    rc = check(cudaMemcpyAsync(const_cast<PeerView*>(pv_dev), &pv, sizeof(PeerView), cudaMemcpyHostToDevice, stream));
   if (rc == FEA_OK) {
     pcg_init_kernel<<<vb, 256, 0, stream>>>(n, b, dinv, x, r, p_own, tol, max_iter, state, partials);
     exchange(0);

@@ -93,6 +93,20 @@ __device__ __forceinline__ double reduce_partials(const double* partials, double
   return block_sum(t, scratch);
 }
 
+// Last block of a PCG SpMV: p.Ap of this rank -> state; with peers, warp 0 also publishes it.
+__device__ __forceinline__ void finish_pap(const double* partials, double* s_red, PcgState* st, const PeerView* pv) {
+  const double s = reduce_partials(partials, s_red);
+  if (threadIdx.x == 0) {
+    st->pap = s;
+    st->counter[0] = 0;
+    s_red[0] = s;
+  }
+  if (pv != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < 32) peer_publish(*pv, 1, st->iter, s_red[0], 0.0);
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(kSpmvThreads) spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr,
                                                             const int32_t* __restrict__ node_colidx,
@@ -119,7 +133,7 @@ template <int D>
 __global__ void __launch_bounds__(kSpmvThreads)
 pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                 const double* __restrict__ values, const double* __restrict__ p, double* __restrict__ ap,
-                int64_t p_row_offset, PcgState* st, double* partials) {
+                int64_t p_row_offset, PcgState* st, double* partials, const PeerView* pv) {
   __shared__ double s_red[32];
   if (st->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -140,13 +154,7 @@ pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const 
     }
   }
   const double total = block_sum(dot, s_red);
-  if (publish_partials(partials, 1, &total, &st->counter[0])) {
-    const double s = reduce_partials(partials, s_red);
-    if (threadIdx.x == 0) {
-      st->pap = s;
-      st->counter[0] = 0;
-    }
-  }
+  if (publish_partials(partials, 1, &total, &st->counter[0])) finish_pap(partials, s_red, st, pv);
 }
 
 // step 1, bulk-copy pipeline variant (spmv_tma.cuh)
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(tma_threads(D, G))
 pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                     const double* __restrict__ values, const double* __restrict__ p, double* __restrict__ ap,
                     const double* __restrict__ p_own, int stages, int val_cap, int col_cap, PcgState* st,
-                    double* partials) {
+                    double* partials, const PeerView* pv) {
   extern __shared__ __align__(128) unsigned char s_tma[];
   __shared__ double s_red[32];
   if (st->done) return;
@@ -163,19 +171,13 @@ pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const 
   spmv_tma_body<D, G, true>(n_nodes, node_rowptr, node_colidx, values, p, ap, p_own, stages, val_cap, col_cap, s_tma,
                             dot);
   const double total = block_sum(dot, s_red);
-  if (publish_partials(partials, 1, &total, &st->counter[0])) {
-    const double s = reduce_partials(partials, s_red);
-    if (threadIdx.x == 0) {
-      st->pap = s;
-      st->counter[0] = 0;
-    }
-  }
+  if (publish_partials(partials, 1, &total, &st->counter[0])) finish_pap(partials, s_red, st, pv);
 }
 
 template <int D, int G>
 static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
                       const double* values, const double* x, double* y, int64_t off, PcgState* st, double* partials,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const PeerView* pv) {
   const TmaLayout& L = plan.layout;
   // Persistent kernel: never launch more CTAs than can be resident at once (a partial second
   // wave would idle most of the chip), whatever registers / shared memory allow for this variant.
@@ -200,7 +202,7 @@ static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int3
       grid_key = key;
     }
     pcg_spmv_tma_kernel<D, G><<<grid_cache, tma_threads(D, G), L.smem_bytes, stream>>>(
-        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials);
+        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, pv);
   } else {
     static int grid_cache = 0;
     static long long grid_key = -1;
@@ -219,23 +221,23 @@ static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int3
 template <int D>
 static int launch_tma_g(const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
                         const double* values, const double* x, double* y, int64_t off, PcgState* st,
-                        double* partials, cudaStream_t stream) {
+                        double* partials, cudaStream_t stream, const PeerView* pv) {
   switch (plan.groups) {
-    case 1: return launch_tma<D, 1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
-    case 2: return launch_tma<D, 2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
-    case 3: return launch_tma<D, 3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
-    case 4: return launch_tma<D, 4>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 1: return launch_tma<D, 1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
+    case 2: return launch_tma<D, 2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
+    case 3: return launch_tma<D, 3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
+    case 4: return launch_tma<D, 4>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
     default: return FEA_ERR_INVALID;
   }
 }
 
 static int dispatch_tma(int d, const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
                         const double* values, const double* x, double* y, int64_t off, PcgState* st,
-                        double* partials, cudaStream_t stream) {
+                        double* partials, cudaStream_t stream, const PeerView* pv = nullptr) {
   switch (d) {
-    case 1: return launch_tma_g<1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
-    case 2: return launch_tma_g<2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
-    case 3: return launch_tma_g<3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream);
+    case 1: return launch_tma_g<1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
+    case 2: return launch_tma_g<2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
+    case 3: return launch_tma_g<3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
     default: return FEA_ERR_INVALID;
   }
 }
@@ -244,10 +246,30 @@ static int dispatch_tma(int d, const TmaPlan& plan, bool dot, int64_t n_nodes, c
 __global__ void __launch_bounds__(256)
 pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ p,
                   const double* __restrict__ ap, double* __restrict__ x, double* __restrict__ r, PcgState* st,
-                  double* partials) {
+                  double* partials, const PeerView* pv) {
   __shared__ double s_red[32];
+  __shared__ double s_glob[2];
+  __shared__ int s_ok;
   if (st->done) return;
-  const double pap = st->pap, rz = st->rz;
+  double pap = st->pap;
+  const double rz = st->rz;
+  const int32_t iter = st->iter;
+  if (pv != nullptr) {  // p.Ap of all ranks: every CTA forms the same rank-ordered sum
+    if (threadIdx.x < 32) {
+      double a, b;
+      const bool ok = peer_collect(*pv, 1, iter, a, b);
+      if (threadIdx.x == 0) {
+        s_glob[0] = a;
+        s_ok = ok;
+      }
+    }
+    __syncthreads();
+    if (!s_ok) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(*pv, st);
+      return;
+    }
+    pap = s_glob[0];
+  }
   if (st->bnorm2 == 0.0 || !(pap > 0.0)) {  // zero right-hand side, or K_ff not positive definite
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       st->done = 1;
@@ -302,10 +324,16 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
     const double a = reduce_partials(partials, s_red);
     const double b = reduce_partials(partials + kMaxPartials, s_red);
     if (threadIdx.x == 0) {
-      st->rz_new = a;
+      st->rz_new = a;  // with peers: this rank's partial sums; the direction kernel stores the global ones
       st->rr = b;
-      st->iter += 1;
+      st->iter = iter + 1;
       st->counter[1] = 0;
+      s_glob[0] = a;
+      s_glob[1] = b;
+    }
+    if (pv != nullptr) {
+      __syncthreads();
+      if (threadIdx.x < 32) peer_publish(*pv, 2, iter, s_glob[0], s_glob[1]);
     }
   }
 }
@@ -313,28 +341,65 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
 // step 3
 __global__ void __launch_bounds__(256)
 pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
-                     double* __restrict__ p, PcgState* st, double* history) {
+                     double* __restrict__ p, PcgState* st, double* history, const PeerView* pv) {
   __shared__ bool s_last;
+  __shared__ double s_glob[2];
+  __shared__ int s_ok;
   if (st->done) return;
-  const double rz = st->rz, rz_new = st->rz_new;
-  const bool converged = st->rr <= st->tol2 * st->bnorm2;
+  const double rz = st->rz;
+  double rz_new = st->rz_new, rr = st->rr;
+  const int32_t iter = st->iter;  // already counts the iteration being finished
+  if (pv != nullptr) {  // r.z and r.r of all ranks
+    if (threadIdx.x < 32) {
+      double a, b;
+      const bool ok = peer_collect(*pv, 2, iter - 1, a, b);
+      if (threadIdx.x == 0) {
+        s_glob[0] = a;
+        s_glob[1] = b;
+        s_ok = ok;
+      }
+    }
+    __syncthreads();
+    if (!s_ok) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(*pv, st);
+      return;
+    }
+    rz_new = s_glob[0];
+    rr = s_glob[1];
+  }
+  const bool converged = rr <= st->tol2 * st->bnorm2;
   if (!converged) {
     const double beta = rz_new / rz;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n; i += 4 * stride) {
-      double di[4], ri[4], pi[4];
+    if (pv == nullptr) {
+      for (; i + 3 * stride < n; i += 4 * stride) {
+        double di[4], ri[4], pi[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t j = i + u * stride;
-        di[u] = dinv[j];
-        ri[u] = r[j];
-        pi[u] = p[j];
+        for (int u = 0; u < 4; ++u) {
+          const int64_t j = i + u * stride;
+          di[u] = dinv[j];
+          ri[u] = r[j];
+          pi[u] = p[j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[i + u * stride] = fma(beta, pi[u], di[u] * ri[u]);
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) p[i + u * stride] = fma(beta, pi[u], di[u] * ri[u]);
+      for (; i < n; i += stride) p[i] = fma(beta, p[i], dinv[i] * r[i]);
+    } else {
+      // the boundary rows of the new p also go straight into the neighbours' halo rows (NVLink stores)
+      const long long lo_off = pv->lower_off, lo_cnt = pv->lower >= 0 ? pv->lower_cnt : 0;
+      const long long up_off = pv->upper_off, up_cnt = pv->upper >= 0 ? pv->upper_cnt : 0;
+      double* lo_dst = pv->lower_dst;
+      double* up_dst = pv->upper_dst;
+      for (; i < n; i += stride) {
+        const double v = fma(beta, p[i], dinv[i] * r[i]);
+        p[i] = v;
+        if ((unsigned long long)(i - lo_off) < (unsigned long long)lo_cnt) lo_dst[i - lo_off] = v;
+        if ((unsigned long long)(i - up_off) < (unsigned long long)up_cnt) up_dst[i - up_off] = v;
+      }
+      __threadfence_system();
     }
-    for (; i < n; i += stride) p[i] = fma(beta, p[i], dinv[i] * r[i]);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -343,20 +408,39 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
   }
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
-    if (history != nullptr && st->iter >= 1 && st->iter <= st->max_iter)
-      history[st->iter - 1] = sqrt(st->rr / st->bnorm2);
+    if (pv != nullptr) {
+      st->rz_new = rz_new;
+      st->rr = rr;
+    }
+    if (history != nullptr && iter >= 1 && iter <= st->max_iter) history[iter - 1] = sqrt(rr / st->bnorm2);
+    bool finished = false;
     if (converged) {
       st->done = 1;
-      st->rr_final = st->rr;
+      st->rr_final = rr;
+      finished = true;
     } else {
       st->rz = rz_new;
-      if (st->iter >= st->max_iter) {
+      if (iter >= st->max_iter) {
         st->done = 1;
         st->status = FEA_ERR_MAXITER;
-        st->rr_final = st->rr;
+        st->rr_final = rr;
       }
     }
     st->counter[2] = 0;
+    if (pv != nullptr && !finished) {
+      // every block's halo stores are fenced (above) and counted: release the iteration tag to the
+      // neighbours, then hold the kernel until their rows of p have landed here, so that the next
+      // SpMV (a plain kernel boundary later) gathers a complete halo.
+      const long long tag = peer_tag(*pv, iter);
+      __threadfence_system();
+      if (pv->lower >= 0) st_release_sys(&pv->hdr[pv->lower]->halo_tag[1], tag);  // I am its upper neighbour
+      if (pv->upper >= 0) st_release_sys(&pv->hdr[pv->upper]->halo_tag[0], tag);
+      CommHeader* own = pv->hdr[pv->rank];
+      bool ok = true;
+      if (pv->lower >= 0) ok = spin_until(&own->halo_tag[0], tag, true) && ok;
+      if (pv->upper >= 0) ok = spin_until(&own->halo_tag[1], tag, true) && ok;
+      if (!ok) peer_failure(*pv, st);
+    }
   }
 }
 
@@ -431,21 +515,21 @@ static PcgWork carve_pcg(void* work, int64_t n) {
 template <int D>
 static int launch_step_spmv(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
                             const double* p, double* ap, int64_t off, PcgState* st, double* partials,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const PeerView* pv) {
   pcg_spmv_kernel<D><<<spmv_blocks(n_nodes), kSpmvThreads, 0, stream>>>(n_nodes, rp, ci, values, p, ap, off, st,
-                                                                        partials);
+                                                                        partials, pv);
   return FEA_OK;
 }
 
 int pcg_step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
                   const double* p, double* ap, int64_t off, PcgState* st, double* partials, cudaStream_t stream,
-                  const TmaPlan* plan) {
+                  const TmaPlan* plan, const PeerView* pv) {
   if (plan != nullptr && plan->ok)
-    return dispatch_tma(d, *plan, true, n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
+    return dispatch_tma(d, *plan, true, n_nodes, rp, ci, values, p, ap, off, st, partials, stream, pv);
   switch (d) {
-    case 1: return launch_step_spmv<1>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
-    case 2: return launch_step_spmv<2>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
-    case 3: return launch_step_spmv<3>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream);
+    case 1: return launch_step_spmv<1>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, pv);
+    case 2: return launch_step_spmv<2>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, pv);
+    case 3: return launch_step_spmv<3>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, pv);
     default: return FEA_ERR_INVALID;
   }
 }
@@ -522,7 +606,7 @@ extern "C" int fea_pcg_step_update(int64_t n_dof, const double* dinv, const doub
                                    double* r, void* state, void* partials, void* stream_) {
   if (!dinv || !p || !ap || !x || !r || !state || !partials || n_dof <= 0) return FEA_ERR_INVALID;
   pcg_update_kernel<<<vec_blocks(n_dof), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      n_dof, dinv, p, ap, x, r, static_cast<PcgState*>(state), static_cast<double*>(partials));
+      n_dof, dinv, p, ap, x, r, static_cast<PcgState*>(state), static_cast<double*>(partials), nullptr);
   return check_launch();
 }
 
@@ -530,7 +614,7 @@ extern "C" int fea_pcg_step_direction(int64_t n_dof, const double* dinv, const d
                                       double* history, void* stream_) {
   if (!dinv || !r || !p || !state || n_dof <= 0) return FEA_ERR_INVALID;
   pcg_direction_kernel<<<vec_blocks(n_dof), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      n_dof, dinv, r, p, static_cast<PcgState*>(state), history);
+      n_dof, dinv, r, p, static_cast<PcgState*>(state), history, nullptr);
   return check_launch();
 }
 
@@ -594,8 +678,8 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     const int r = pcg_step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream,
                             &plan);
     if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
-    pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials);
-    pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history);
+    pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials, nullptr);
+    pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history, nullptr);
     return r;
   };
   // One iteration is launched directly (it carries the timing sample), the other chunk-1 are one

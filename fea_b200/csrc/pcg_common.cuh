@@ -26,6 +26,109 @@ static_assert(sizeof(PcgState) == FEA_PCG_STATE_BYTES, "PcgState layout");
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---------------------------------------------------------------------------------------------
+// NVLink peer-memory exchange primitives of the multi-GPU solver (p2p.cu).  Every rank owns a
+// communication block (header + halo-extended p) that all peers map through CUDA IPC.
+//   * scalars: rank s stores its partial sum(s) and an iteration tag into slot [parity][kind][s] of
+//     EVERY rank's header (peer_publish, one warp, lane r -> rank r); a consumer polls the slots of
+//     its OWN header (local L2) and adds the world values in rank order (peer_collect): every rank
+//     and every CTA gets the bitwise identical sum, no atomics;
+//   * halo: boundary rows of p are stored straight into the neighbour's p vector, then a tag.
+// Tags are (epoch << 32 | iteration + 1); slots are double-buffered by iteration parity.  A rank can
+// never be two exchanges ahead of a peer, because every exchange needs every rank's contribution.
+constexpr int kMaxPeers = FEA_MAX_PEERS;
+constexpr size_t kCommHeaderBytes = 4096;
+constexpr size_t kCommViewOffset = 3584;  // device copy of this rank's PeerView inside its own header
+
+struct PeerSlot {
+  double v[2];
+  long long tag;
+  long long pad;
+};
+struct CommHeader {
+  PeerSlot slots[2][3][kMaxPeers];  // [parity][kind][source rank]
+  long long halo_tag[2];            // [0] written by the lower neighbour, [1] by the upper one
+  unsigned int counter;             // last-block ticket of the halo kernel
+  int error;
+};
+static_assert(sizeof(CommHeader) <= kCommViewOffset, "comm header");
+
+struct PeerView {
+  int world, rank, lower, upper;
+  CommHeader* hdr[kMaxPeers];
+  double* lower_dst;        // neighbour's halo rows that mirror my lowest / highest owned rows
+  double* upper_dst;
+  const double* lower_src;  // = p_own + lower_off
+  const double* upper_src;
+  long long lower_cnt, upper_cnt;  // doubles
+  long long lower_off, upper_off;  // offsets of the mirrored ranges inside p_own (doubles)
+  long long epoch;
+};
+static_assert(sizeof(PeerView) <= kCommHeaderBytes - kCommViewOffset, "PeerView fits the header page");
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded spin (about 2 s): true when *p reaches `want` (exactly, or at least with `at_least`).
+__device__ __forceinline__ bool spin_until(const long long* p, long long want, bool at_least) {
+  for (int i = 0; i < (1 << 24); ++i) {
+    const long long v = ld_acquire_sys(p);
+    if (at_least ? v >= want : v == want) return true;
+    __nanosleep(100);
+  }
+  return false;
+}
+__device__ __forceinline__ long long peer_tag(const PeerView& pv, long long k) { return (pv.epoch << 32) | (k + 1); }
+// A peer never delivered: stop the solve with FEA_ERR_PEER instead of hanging the GPU.
+__device__ __forceinline__ void peer_failure(const PeerView& pv, PcgState* st) {
+  pv.hdr[pv.rank]->error = 1;
+  st->status = FEA_ERR_PEER;
+  st->done = 1;
+  st->rr_final = st->rr;
+}
+
+// One full warp: lane r stores (v0, v1, tag) into rank r's slot for this rank.
+__device__ __forceinline__ void peer_publish(const PeerView& pv, int kind, long long k, double v0, double v1) {
+  const int lane = threadIdx.x & 31;
+  if (lane < pv.world) {
+    PeerSlot* dst = &pv.hdr[lane]->slots[(int)(k & 1)][kind][pv.rank];
+    dst->v[0] = v0;
+    dst->v[1] = v1;
+    __threadfence_system();
+    st_release_sys(&dst->tag, peer_tag(pv, k));
+  }
+}
+// One full warp: waits for every rank's slot of exchange (kind, k) in the own header and returns the
+// rank-ordered sums in all lanes; false if a peer never arrived.
+__device__ __forceinline__ bool peer_collect(const PeerView& pv, int kind, long long k, double& s0, double& s1) {
+  const int lane = threadIdx.x & 31;
+  double v0 = 0.0, v1 = 0.0;
+  bool ok = true;
+  if (lane < pv.world) {
+    const PeerSlot* src = &pv.hdr[pv.rank]->slots[(int)(k & 1)][kind][lane];
+    ok = spin_until(&src->tag, peer_tag(pv, k), false);
+    v0 = ld_volatile_f64(&src->v[0]);
+    v1 = ld_volatile_f64(&src->v[1]);
+  }
+  ok = __all_sync(kFull, ok);
+  s0 = s1 = 0.0;
+  for (int r = 0; r < pv.world; ++r) {
+    s0 += __shfl_sync(kFull, v0, r);
+    s1 += __shfl_sync(kFull, v1, r);
+  }
+  return ok;
+}
+
 inline unsigned vec_blocks(int64_t n) {
   // 8 resident CTAs of 256 threads per SM, one full wave (<= kMaxPartials blocks)
   const int64_t b = (n + 256 * 4 - 1) / (256 * 4);
@@ -33,11 +136,13 @@ inline unsigned vec_blocks(int64_t n) {
 }
 
 // Solver kernels defined in pcg.cu, launched by both drivers.
+// `pv` (device pointer, may be null): with a PeerView the dot products are exchanged with the
+// peer ranks inside these kernels and the direction kernel pushes the halo rows (see p2p.cu).
 __global__ void __launch_bounds__(256) pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ p,
                                   const double* __restrict__ ap, double* __restrict__ x, double* __restrict__ r,
-                                  PcgState* st, double* partials);
+                                  PcgState* st, double* partials, const PeerView* pv);
 __global__ void __launch_bounds__(256) pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
-                                     double* __restrict__ p, PcgState* st, double* history);
+                                     double* __restrict__ p, PcgState* st, double* history, const PeerView* pv);
 __global__ void __launch_bounds__(256) pcg_init_kernel(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
                                 double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, double tol,
                                 int max_iter, PcgState* st, double* partials);
@@ -45,7 +150,7 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(int64_t n, const double* 
 // step 1 (ap = K p over `n_nodes` rows, p.ap into state) on the best available kernel.
 int pcg_step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
                   const double* p, double* ap, int64_t p_row_offset, PcgState* st, double* partials,
-                  cudaStream_t stream, const TmaPlan* plan);
+                  cudaStream_t stream, const TmaPlan* plan, const PeerView* pv = nullptr);
 void pcg_match_carveout();
 
 }  // namespace fea

@@ -389,16 +389,29 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
     (u_owned (n_owned,3) device, reactions_owned device, DistInfo, BlockCSR)."""
     from . import core
 
+    prof = STAGE_PROFILE if STAGE_PROFILE.get("enabled") else None
+
+    def mark(name, t0):
+        if prof is None:
+            return t0
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        prof[name] = prof.get(name, 0.0) + (t1 - t0) * 1e3
+        return t1
+
+    t = time.perf_counter()
     g_lo, g_hi = plan.g_lo, plan.g_hi
     nodes_d = core.to_device(np.ascontiguousarray(nodes[g_lo:g_hi]), torch.float64)
     el_local = np.ascontiguousarray(elements[plan.element_ids] - g_lo)
     elements_d = core.to_device(el_local, torch.int32)
     fixed = core._fixed_mask(np.ascontiguousarray(np.asarray(constraints)[g_lo:g_hi]), 3 * plan.n_local)
+    t = mark("slice_h2d", t)
     K = core.assemble_hex8(nodes_d, elements_d, E, nu, fixed=fixed)
     lo, hi = 3 * plan.offset, 3 * (plan.offset + plan.n_owned)
     dinv_owned = K.dinv[lo:hi].contiguous()
     b_owned = core.to_device(np.ascontiguousarray(np.asarray(forces)[plan.own_lo:plan.own_hi]),
                              torch.float64).reshape(-1)
+    t = mark("symbolic_assembly", t)
     ops = GpuOps(K, plan)
     if max_iter is None:
         max_iter = 10 * 3 * int(np.asarray(nodes).shape[0])
@@ -407,13 +420,20 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
         x, info = p2p_pcg(K, plan, b_owned, dinv_owned, tol, max_iter, group=group)
     else:
         x, info = distributed_pcg(ops, plan, 3, b_owned, dinv_owned, tol=tol, max_iter=max_iter, group=group)
+    t = mark("pcg", t)
     # reactions: K_full u on the owned rows needs u on the halo
     u_ext = torch.zeros(3 * plan.n_local, dtype=torch.float64, device=x.device)
     u_ext[lo:hi] = x
     HaloExchange(plan, 3, group)(u_ext)
     reactions = torch.empty_like(x)
     ops.matvec_owned(u_ext, reactions)
+    mark("reactions", t)
     return x.reshape(-1, 3), reactions.reshape(-1, 3), info, K
+
+
+# stage timings of solve_hex8_slab (ms, accumulated; each stage ends with a device synchronise) when
+# STAGE_PROFILE["enabled"] is set -- bench.py switches it on for ONE extra untimed step.
+STAGE_PROFILE: dict = {"enabled": False}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -463,6 +483,13 @@ def bench_entry(args, A, b, tol, E, nu, measured_peaks, ClockSampler, cpu_sample
     ms_per_step = float(ms)
     prof = (4 * __import__("ctypes").c_double)()
     lib.fea_profile_read(prof)
+    # one more, untimed, step with a synchronise after every stage: where a step's time goes
+    STAGE_PROFILE.clear()
+    STAGE_PROFILE["enabled"] = True
+    barrier()
+    step()
+    STAGE_PROFILE["enabled"] = False
+    stages = {k: round(v, 3) for k, v in STAGE_PROFILE.items() if k != "enabled"}
     info, K = out["info"], out["K"]
     # SpMV kernel alone on this rank's slab (CUDA events, after the timed region)
     p_ext = torch.randn(3 * plan.n_local, dtype=torch.float64, device="cuda")
@@ -504,6 +531,7 @@ def bench_entry(args, A, b, tol, E, nu, measured_peaks, ClockSampler, cpu_sample
                          "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak,
                          "traffic": None, "peak_source": peak_src, "aggregate_gb_per_s": float(agg),
                          "slowest_rank_ms": float(stats[0])},
+            "stages_ms_rank0": stages,
             "cpu_baseline": None,
             "e2e": {"value": n_free / (ms_per_step / 1e3), "unit": "solved DOF/s",
                     "h2d_bytes_per_step": int(nodes[plan.g_lo:plan.g_hi].nbytes + plan.element_ids.size * 64

@@ -34,16 +34,20 @@ ONCE = "--once" in sys.argv  # single launches, no warm-up: the pass that runs u
 
 
 def timed(fn, reps=1):
+    """(result, best ms over `reps` individually timed calls).  Boxes of the pool show 2-4x run-to-run
+    noise on ~1 ms kernels (power management), so the minimum is the comparable figure."""
     if ONCE:
         reps = 1
-    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    a.record()
+    best = float("inf")
     for _ in range(reps):
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
         out = fn()
-    c.record()
-    torch.cuda.synchronize()
-    return out, a.elapsed_time(c) / reps
+        c.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(c))
+    return out, best
 
 
 def device_mesh(A, b):
@@ -66,7 +70,7 @@ def ke_bench(M):
             nd += torch.from_numpy(rng.uniform(-jitter * h, jitter * h, size=tuple(nd.shape))).to(nd.device)
         for _ in range(0 if ONCE else 2):
             utils.hexahedral_stiffness_matrices(nd, elements, E_HEX, NU_HEX)
-        _, ms = timed(lambda: utils.hexahedral_stiffness_matrices(nd, elements, E_HEX, NU_HEX), 5)
+        _, ms = timed(lambda: utils.hexahedral_stiffness_matrices(nd, elements, E_HEX, NU_HEX), 20)
         out[label] = {"ms": ms, "elem_per_s": M / ms * 1e3, "tflops_at_21kflop": 21e3 * M / ms / 1e9,
                       "write_gb_per_s": 4608 * M / ms / 1e6}
     print(json.dumps({"bench": "ke_hex8", "elements": M, **out}), flush=True)
@@ -83,7 +87,7 @@ def asm_bench(A, b):
         pat = core.symbolic(elements, nodes.shape[0])
         K = core.assemble_hex8(nodes, elements, E_HEX, NU_HEX, pattern=pat, fixed=fixed)
     pat, ms_sym = timed(lambda: core.symbolic(elements, nodes.shape[0]), 3)
-    K, ms_num = timed(lambda: core.assemble_hex8(nodes, elements, E_HEX, NU_HEX, pattern=pat, fixed=fixed), 5)
+    K, ms_num = timed(lambda: core.assemble_hex8(nodes, elements, E_HEX, NU_HEX, pattern=pat, fixed=fixed), 10)
     M, N = elements.shape[0], nodes.shape[0]
     alg = 8 * K.nnz + 24 * N + 32 * M
     print(json.dumps({"bench": "assemble_hex8", "mesh": [A, b, b], "elements": M, "nnz": K.nnz,
@@ -104,8 +108,13 @@ def spmv_bench(nodes, K, reps):
         K.matvec(x, out=y)
     groups = []
     for _ in range(max(1, reps // 200)):
-        _, ms = timed(lambda: K.matvec(x, out=y), 200)
-        groups.append(round(ms, 4))
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(1 if ONCE else 200):
+            K.matvec(x, out=y)
+        c.record()
+        torch.cuda.synchronize()
+        groups.append(round(a.elapsed_time(c) / (1 if ONCE else 200), 4))
     alg = 12 * K.nnz + 20 * K.n_dof
     lib = _lib.load()
     lib.fea_profile_enable(1)
@@ -130,7 +139,7 @@ def multi_bench(n, n_rhs, iters):
     if not ONCE:
         K.matmat(B)
     Yout = torch.empty_like(B)
-    spmm_rounds = [timed(lambda: K.matmat(B, out=Yout), 10)[1] for _ in range(1 if ONCE else 5)]
+    spmm_rounds = [timed(lambda: K.matmat(B, out=Yout), 4)[1] for _ in range(1 if ONCE else 5)]
     ms_spmm = min(spmm_rounds)
     if not ONCE:
         core.pcg_multi(K, B, tol=1e-12, max_iter=16, raise_on_failure=False)
