@@ -176,3 +176,46 @@ def test_multi_rhs_matches_single():
         x, it, _ = fo.jacobi_pcg(A, B[:, j], tol=1e-12)
         assert abs(it - iters[j]) <= 3  # dot-product summation order differs (einsum vs @)
         assert rel(X[:, j], x) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle/fea_oracle_c.c (OpenMP C restatement, the multi-core CPU baseline of bench.py): pinned to
+# the same reference-generated fixtures and to the numpy oracle.
+# ------------------------------------------------------------------------------------------------
+def test_c_oracle_ke_golden(golden):
+    from oracle import c_oracle as co
+
+    g = golden("hex8_single.npz")
+    assert rel(co.hex8_ke_batched(g["cube"], np.arange(8)[None], 1000, 0.0)[0], g["ke_cube"]) < 1e-14
+    E, nu = float(g["E"]), float(g["nu"])
+    nodes = g["dist_nodes"].reshape(-1, 3)
+    elements = np.arange(nodes.shape[0]).reshape(-1, 8)
+    assert rel(co.hex8_ke_batched(nodes, elements, E, nu), g["ke_dist"]) < 1e-12
+    with pytest.raises(ValueError, match="Jacobian determinant is non-positive"):
+        co.hex8_ke_batched(g["inverted"], np.arange(8)[None], 1000, 0.0)
+
+
+def test_c_oracle_assembly_and_pcg_vs_numpy_oracle(golden):
+    from oracle import c_oracle as co
+
+    g = golden("cubebeam.npz")
+    nodes, elements, cons, forces = fo.cubebeam_case()
+    ip, ix = fo.structural_pattern(elements, nodes.shape[0], 3)
+    ip2, ix2 = co.dof_pattern(elements, nodes.shape[0], 3)
+    assert np.array_equal(ip, ip2) and np.array_equal(ix, ix2)
+    K = fo.assemble_csr(elements, fo.hex8_ke_batched(nodes, elements, fo.E_HEX, fo.NU_HEX), nodes.shape[0], 3)
+    Kc = co.assemble_hex8(nodes, elements, fo.E_HEX, fo.NU_HEX)
+    assert np.array_equal(K.indptr, Kc.indptr) and np.array_equal(K.indices, Kc.indices)
+    assert rel(Kc.data, K.data) < 1e-13
+    x = np.random.default_rng(0).standard_normal(K.shape[0])
+    assert rel(co.spmv(Kc, x), K @ x) < 1e-13
+    free = fo.free_dofs(cons)
+    Kff, ff = Kc[free][:, free].tocsr(), forces.flatten()[free]
+    u, it, relres = co.jacobi_pcg(Kff, ff, tol=1e-12)
+    un, itn, _ = fo.jacobi_pcg(Kff, ff, tol=1e-12)
+    assert relres <= 1e-12 and abs(it - itn) <= max(5, itn // 20)
+    assert rel(u, un) < 1e-8
+    # and against the reference's own displacements (K5 fixture)
+    full = np.zeros(K.shape[0])
+    full[free] = u
+    assert rel(full.reshape(-1, 3), g["displacements"]) < 1e-8
