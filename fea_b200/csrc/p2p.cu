@@ -147,6 +147,10 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   double* r = reinterpret_cast<double*>(c);
   c += vec;
   double* ap = reinterpret_cast<double*>(c);
+  c += vec;
+  double* p2 = reinterpret_cast<double*>(c);  // single-reduction variant: search direction and s = K p
+  c += vec;
+  double* s_vec = reinterpret_cast<double*>(c);
 
   PeerView pv;
   std::memset(&pv, 0, sizeof(pv));
@@ -203,14 +207,21 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     if (multi) p2p_halo_kernel<<<halo_blocks, 256, 0, stream>>>(pv, state);
   };
   const PeerView* pv_it = multi ? pv_dev : nullptr;
+  const int algo = pcg_algorithm(n, multi);
   auto iteration = [&]() -> int {
     const int r1 = pcg_step_spmv(d, n_owned_nodes, node_rowptr_owned, node_colidx, values, p_ext, ap,
                                  comm->own_offset_nodes, state, partials, stream, &plan, pv_it);
-    pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials, pv_it);
-    pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, nullptr, pv_it);
+    if (algo == 1) {  // p_own holds u = dinv r here (the SpMV input)
+      pcg_cgcg_kernel<<<cgcg_blocks(n), 256, 0, stream>>>(n, dinv, p_own, ap, p2, s_vec, x, r, state, partials, nullptr,
+                                                          pv_it);
+    } else {
+      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials, pv_it);
+      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, nullptr, pv_it);
+    }
     return r1;
   };
-  const int launches_per_iteration = 3;
+  const int launches_per_iteration = algo == 1 ? 2 : 3;
+  const int64_t enqueue_limit = (int64_t)max_iter + (algo == 1 ? 1 : 0);
 
   if (rc == FEA_OK) {
     pcg_match_carveout();
@@ -225,7 +236,8 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     rc = check_launch(multi ? 3 : 1);
   }
   const int chunk = 32;
-  int enqueued = 0, slot = 0;
+  int64_t enqueued = 0;
+  int slot = 0;
   bool pending[2] = {false, false};
   bool finished = false;
   if (rc == FEA_OK && max_iter >= chunk && std::getenv("FEA_PCG_NO_GRAPH") == nullptr) {
@@ -243,7 +255,7 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     cudaGetLastError();
   }
   while (rc == FEA_OK && !finished) {
-    const int todo = std::min(chunk, max_iter - enqueued);
+    const int todo = (int)std::min<int64_t>(chunk, enqueue_limit - enqueued);
     if (graph_exec != nullptr && todo == chunk) {
       rc = check(cudaGraphLaunch(graph_exec, stream));
     } else {
@@ -263,7 +275,7 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
       pending[prev] = false;
       if (rc == FEA_OK && snap[prev].done) finished = true;
     }
-    if (!finished && enqueued >= max_iter) finished = true;
+    if (!finished && enqueued >= enqueue_limit) finished = true;
     slot ^= 1;
   }
   if (rc == FEA_OK) {

@@ -444,6 +444,157 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-reduction variant (Chronopoulos & Gear 1989), FEA_PCG_ALGO=1: the same iterates as the
+// classical recurrence in exact arithmetic, with TWO kernels and ONE dependent reduction per
+// iteration instead of three and two:
+//   step 1  w = K u            + partial delta = u.w          (the SpMV kernels above; u = dinv r)
+//   step 2  beta = gamma/gamma_old, alpha = gamma / (delta - beta gamma / alpha_old)
+//           p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  u = dinv r
+//           + partial gamma' = r.u and r.r                              (this kernel)
+// Convergence of iteration k is known once its r.r has been reduced, i.e. at the start of step 2 of
+// iteration k+1: the solve spends one extra SpMV.  Small meshes are launch-bound (3 kernels cost
+// ~33 us per iteration at 133 k DOF, the SpMV itself 17 us), and across GPUs every reduction is a
+// cross-rank synchronisation point; at 7.9 M DOF on one GPU the variant is neutral (12 instead of
+// 11 vector passes, one launch less).  State: rz = gamma_old, rz_new = gamma, pap = delta,
+// spare[0] = alpha_old.
+__global__ void __launch_bounds__(256, 3)
+pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__ u, const double* __restrict__ w,
+                double* __restrict__ p, double* __restrict__ s, double* __restrict__ x, double* __restrict__ r,
+                PcgState* st, double* partials, double* history, const PeerView* pv) {
+  __shared__ double s_red[32];
+  __shared__ double s_glob[3];
+  __shared__ int s_ok;
+  if (st->done) return;
+  const int32_t iter = st->iter;  // iterations completed so far
+  double gamma = iter == 0 ? st->rz : st->rz_new;
+  double rr = st->rr, delta = st->pap;
+  if (pv != nullptr) {  // world sums: u.w of this iteration, (r.u, r.r) of the previous one
+    if (threadIdx.x < 32) {
+      double a, c, d;
+      const bool ok = peer_collect2(*pv, 1, iter, 2, (long long)iter - 1, a, c, d);
+      if (threadIdx.x == 0) {
+        s_glob[0] = a;
+        s_glob[1] = c;
+        s_glob[2] = d;
+        s_ok = ok;
+      }
+    }
+    __syncthreads();
+    if (!s_ok) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(*pv, st);
+      return;
+    }
+    delta = s_glob[0];
+    if (iter > 0) {
+      gamma = s_glob[1];
+      rr = s_glob[2];
+    }
+  }
+  const double bnorm2 = st->bnorm2;
+  const bool converged = rr <= st->tol2 * bnorm2;  // also covers a zero right-hand side
+  const bool exhausted = !converged && iter >= st->max_iter;
+  double beta = 0.0, alpha = 0.0;
+  bool breakdown = false;
+  if (!converged && !exhausted) {
+    if (iter == 0) {
+      breakdown = !(delta > 0.0);
+      alpha = gamma / delta;
+    } else {
+      beta = gamma / st->rz;
+      const double denom = delta - beta * gamma / st->spare[0];
+      breakdown = !(denom > 0.0);
+      alpha = gamma / denom;
+    }
+  }
+  if (converged || exhausted || breakdown) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      if (history != nullptr && iter >= 1 && iter <= st->max_iter) history[iter - 1] = sqrt(rr / bnorm2);
+      st->done = 1;
+      st->status = converged ? FEA_OK : (breakdown ? FEA_ERR_BREAKDOWN : FEA_ERR_MAXITER);
+      st->rr = rr;
+      st->rr_final = rr;
+    }
+    return;
+  }
+  double s_ru = 0.0, s_rr = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const long long lo_off = pv ? pv->lower_off : 0, lo_cnt = pv && pv->lower >= 0 ? pv->lower_cnt : 0;
+  const long long up_off = pv ? pv->upper_off : 0, up_cnt = pv && pv->upper >= 0 ? pv->upper_cnt : 0;
+  double* lo_dst = pv ? pv->lower_dst : nullptr;
+  double* up_dst = pv ? pv->upper_dst : nullptr;
+  auto finish = [&](int64_t j, double di, double uj, double wj, double pj, double sj, double xj, double rj) {
+    const double pn = iter == 0 ? uj : fma(beta, pj, uj);
+    const double sn = iter == 0 ? wj : fma(beta, sj, wj);
+    const double rn = fma(-alpha, sn, rj);
+    const double un = di * rn;
+    p[j] = pn;
+    s[j] = sn;
+    __stcs(x + j, fma(alpha, pn, xj));
+    r[j] = rn;
+    u[j] = un;
+    if (pv != nullptr) {  // boundary rows of the new u go straight into the neighbours' halo rows
+      if ((unsigned long long)(j - lo_off) < (unsigned long long)lo_cnt) lo_dst[j - lo_off] = un;
+      if ((unsigned long long)(j - up_off) < (unsigned long long)up_cnt) up_dst[j - up_off] = un;
+    }
+    if (di != 0.0) {
+      s_ru = fma(rn, un, s_ru);
+      s_rr = fma(rn, rn, s_rr);
+    }
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) {  // two elements in flight: 14 independent loads
+    const int64_t j0 = i, j1 = i + stride;
+    const double d0 = dinv[j0], u0 = u[j0], w0 = __ldcs(w + j0), r0 = r[j0], x0 = __ldcs(x + j0);
+    const double d1 = dinv[j1], u1 = u[j1], w1 = __ldcs(w + j1), r1 = r[j1], x1 = __ldcs(x + j1);
+    double p0 = 0.0, q0 = 0.0, p1 = 0.0, q1 = 0.0;
+    if (iter != 0) {
+      p0 = p[j0];
+      q0 = s[j0];
+      p1 = p[j1];
+      q1 = s[j1];
+    }
+    finish(j0, d0, u0, w0, p0, q0, x0, r0);
+    finish(j1, d1, u1, w1, p1, q1, x1, r1);
+  }
+  for (; i < n; i += stride)
+    finish(i, dinv[i], u[i], w[i], iter != 0 ? p[i] : 0.0, iter != 0 ? s[i] : 0.0, x[i], r[i]);
+  if (pv != nullptr) __threadfence_system();
+  double tot[2];
+  tot[0] = block_sum(s_ru, s_red);
+  tot[1] = block_sum(s_rr, s_red);
+  if (publish_partials(partials, 2, tot, &st->counter[1])) {
+    const double a = reduce_partials(partials, s_red);
+    const double b = reduce_partials(partials + kMaxPartials, s_red);
+    if (threadIdx.x == 0) {
+      if (history != nullptr && iter >= 1 && iter <= st->max_iter) history[iter - 1] = sqrt(rr / bnorm2);
+      st->rz = gamma;    // gamma_old of the next iteration
+      st->rz_new = a;    // with peers: this rank's partial sums (the next step 2 collects the world's)
+      st->rr = b;
+      st->spare[0] = alpha;
+      st->iter = iter + 1;
+      st->counter[1] = 0;
+      s_glob[0] = a;
+      s_glob[1] = b;
+    }
+    if (pv != nullptr) {
+      __syncthreads();
+      if (threadIdx.x < 32) peer_publish(*pv, 2, iter, s_glob[0], s_glob[1]);
+      if (threadIdx.x == 0) {
+        const long long tag = peer_tag(*pv, iter + 1);
+        __threadfence_system();
+        if (pv->lower >= 0) st_release_sys(&pv->hdr[pv->lower]->halo_tag[1], tag);
+        if (pv->upper >= 0) st_release_sys(&pv->hdr[pv->upper]->halo_tag[0], tag);
+        CommHeader* own = pv->hdr[pv->rank];
+        bool ok = true;
+        if (pv->lower >= 0) ok = spin_until(&own->halo_tag[0], tag, true) && ok;
+        if (pv->upper >= 0) ok = spin_until(&own->halo_tag[1], tag, true) && ok;
+        if (!ok) peer_failure(*pv, st);
+      }
+    }
+  }
+}
+
 // x = 0, r = b on free DOF (0 on constrained), p = dinv r; partial r.z and ||b||^2.
 __global__ void __launch_bounds__(256)
 pcg_init_kernel(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
@@ -492,8 +643,10 @@ struct PcgWork {
   PcgState* state;
   double* partials;  // 2 * kMaxPartials
   double* r;
-  double* p;
-  double* ap;
+  double* p;   // classical: search direction; single-reduction variant: u = dinv r (the SpMV input)
+  double* ap;  // SpMV output
+  double* p2;  // single-reduction variant only: search direction p and s = K p
+  double* s;
 };
 
 static PcgWork carve_pcg(void* work, int64_t n) {
@@ -509,7 +662,23 @@ static PcgWork carve_pcg(void* work, int64_t n) {
   w.p = reinterpret_cast<double*>(c);
   c += vec;
   w.ap = reinterpret_cast<double*>(c);
+  c += vec;
+  w.p2 = reinterpret_cast<double*>(c);
+  c += vec;
+  w.s = reinterpret_cast<double*>(c);
   return w;
+}
+
+int pcg_algorithm(int64_t n_dof, bool multi_gpu) {  // read per solve, so that a process can switch (tests do)
+  const char* env = std::getenv("FEA_PCG_ALGO");
+  if (env != nullptr && (env[0] == '0' || env[0] == '1')) return env[0] - '0';
+  // The single-reduction variant trades one kernel boundary / one cross-rank synchronisation per
+  // iteration for one more vector pass (8 n bytes); n is the per-rank size.  Measured on B200
+  // (400x80x80 unless noted): one GPU 133 k DOF -12 %, one GPU 7.9 M DOF +2 %; two GPUs (3.9 M DOF per
+  // rank) +0.5 %; eight GPUs (1 M DOF per rank) -8.9 % (1.417 -> 1.291 s).  The vector kernel must run
+  // as ONE resident wave: with 4 waves of CTAs each polling the peer slots it lost 19 % on 8 GPUs.
+  (void)multi_gpu;
+  return n_dof < kSingleReductionBelowDof ? 1 : 0;
 }
 
 template <int D>
@@ -560,7 +729,7 @@ extern "C" int fea_spmv(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, 
 }
 
 extern "C" size_t fea_pcg_workspace(int64_t n_dof) {
-  return FEA_PCG_STATE_BYTES + sizeof(double) * 2 * kMaxPartials + 3 * align_up(sizeof(double) * (size_t)n_dof, 256);
+  return FEA_PCG_STATE_BYTES + sizeof(double) * 2 * kMaxPartials + 5 * align_up(sizeof(double) * (size_t)n_dof, 256);
 }
 
 // The SpMV kernel wants (almost) the whole SM array as shared memory; the vector kernels of the
@@ -576,6 +745,7 @@ void fea::pcg_match_carveout() {
   cudaFuncSetAttribute(pcg_direction_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                        cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(pcg_init_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(pcg_cgcg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 extern "C" int fea_pcg_init(int64_t n_dof, const double* b, const double* dinv, double* x, double* r, double* p,
@@ -660,7 +830,12 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   rc = fea_pcg_init(n, b, dinv, x, w.r, w.p, tol, max_iter, w.state, w.partials, stream);
   const unsigned vb = vec_blocks(n);
   const int chunk = 32;
-  int enqueued = 0, slot = 0;
+  const int algo = pcg_algorithm(n, false);
+  const int per_iter = algo == 1 ? 2 : 3;  // kernels per iteration
+  // the single-reduction variant learns about convergence / max_iter one step later
+  const int64_t enqueue_limit = (int64_t)max_iter + (algo == 1 ? 1 : 0);
+  int64_t enqueued = 0;
+  int slot = 0;
   bool pending[2] = {false, false};
   bool finished = false;
   // measurement hook: CUDA-event pairs around the first SpMV launch of each chunk
@@ -673,13 +848,18 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   }
   int sample_iter[kMaxSamples];
   auto enqueue_iteration = [&](bool sample) -> int {
-    if (sample) sample_iter[n_samples] = enqueued;  // 0-based index of the iteration being timed
+    if (sample) sample_iter[n_samples] = (int)enqueued;  // 0-based index of the iteration being timed
     if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
     const int r = pcg_step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream,
                             &plan);
     if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
-    pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials, nullptr);
-    pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history, nullptr);
+    if (algo == 1) {
+      pcg_cgcg_kernel<<<cgcg_blocks(n), 256, 0, stream>>>(n, dinv, w.p, w.ap, w.p2, w.s, x, w.r, w.state, w.partials,
+                                                          history, nullptr);
+    } else {
+      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials, nullptr);
+      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history, nullptr);
+    }
     return r;
   };
   // One iteration is launched directly (it carries the timing sample), the other chunk-1 are one
@@ -688,7 +868,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   cudaGraphExec_t graph_exec = nullptr;
   if (own != nullptr && rc == FEA_OK && max_iter >= chunk) {
     enqueue_iteration(false);  // warm: every cudaFuncSetAttribute / occupancy query happens outside capture
-    rc = check_launch(3);
+    rc = check_launch(per_iter);
     enqueued += 1;
     cudaGraph_t graph = nullptr;
     if (rc == FEA_OK && cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -701,7 +881,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     cudaGetLastError();  // a failed capture falls back to plain launches
   }
   while (rc == FEA_OK && !finished) {
-    const int todo = std::min(chunk, max_iter - enqueued);
+    const int todo = (int)std::min<int64_t>(chunk, enqueue_limit - enqueued);
     if (graph_exec != nullptr && todo == chunk) {
       rc = enqueue_iteration(sample_ev != nullptr && n_samples < kMaxSamples);
       if (rc == FEA_OK) rc = check(cudaGraphLaunch(graph_exec, stream));
@@ -709,7 +889,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
       for (int it = 0; it < todo && rc == FEA_OK; ++it)
         rc = enqueue_iteration(sample_ev != nullptr && it == 0 && n_samples < kMaxSamples);
     }
-    if (rc == FEA_OK) rc = check_launch(3 * todo);
+    if (rc == FEA_OK) rc = check_launch(per_iter * todo);
     if (rc != FEA_OK) break;
     enqueued += todo;
     rc = check(cudaMemcpyAsync(&snap[slot], w.state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
@@ -723,7 +903,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
       pending[prev] = false;
       if (rc == FEA_OK && snap[prev].done) finished = true;
     }
-    if (!finished && enqueued >= max_iter) {
+    if (!finished && enqueued >= enqueue_limit) {
       rc = check(cudaEventSynchronize(ev[slot]));
       pending[slot] = false;
       finished = true;

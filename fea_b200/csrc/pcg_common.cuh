@@ -129,10 +129,46 @@ __device__ __forceinline__ bool peer_collect(const PeerView& pv, int kind, long 
   return ok;
 }
 
+// Grid of the single-reduction vector kernel: ONE resident wave (3 CTAs per SM), every CTA polls the
+// peer slots exactly once.
+inline unsigned cgcg_blocks(int64_t n) {
+  const int64_t b = (n + 256 * 2 - 1) / (256 * 2);
+  return (unsigned)(b < 1 ? 1 : (b > 148LL * 3 ? 148LL * 3 : b));
+}
+
 inline unsigned vec_blocks(int64_t n) {
   // 8 resident CTAs of 256 threads per SM, one full wave (<= kMaxPartials blocks)
   const int64_t b = (n + 256 * 4 - 1) / (256 * 4);
   return (unsigned)(b < 1 ? 1 : (b > 148LL * 8 ? 148LL * 8 : b));
+}
+
+// One full warp, two exchanges polled at once: lanes [0, world) wait for exchange (kind_a, ka), lanes
+// [kMaxPeers, kMaxPeers + world) for (kind_b, kb) (skipped when kb < 0).  a0 = sum of v[0] of the first,
+// b0 / b1 = sums of v[0] / v[1] of the second, all in rank order, in all lanes.
+__device__ __forceinline__ bool peer_collect2(const PeerView& pv, int kind_a, long long ka, int kind_b, long long kb,
+                                              double& a0, double& b0, double& b1) {
+  static_assert(2 * kMaxPeers <= 32, "two exchanges fit one warp");
+  const int lane = threadIdx.x & 31;
+  const bool second = lane >= kMaxPeers;
+  const int src_rank = second ? lane - kMaxPeers : lane;
+  const bool mine = src_rank < pv.world && lane < 2 * kMaxPeers && (!second || kb >= 0);
+  double v0 = 0.0, v1 = 0.0;
+  bool ok = true;
+  if (mine) {
+    const long long k = second ? kb : ka;
+    const PeerSlot* src = &pv.hdr[pv.rank]->slots[(int)(k & 1)][second ? kind_b : kind_a][src_rank];
+    ok = spin_until(&src->tag, peer_tag(pv, k), false);
+    v0 = ld_volatile_f64(&src->v[0]);
+    v1 = ld_volatile_f64(&src->v[1]);
+  }
+  ok = __all_sync(kFull, ok);
+  a0 = b0 = b1 = 0.0;
+  for (int r = 0; r < pv.world; ++r) {
+    a0 += __shfl_sync(kFull, v0, r);
+    b0 += __shfl_sync(kFull, v0, kMaxPeers + r);
+    b1 += __shfl_sync(kFull, v1, kMaxPeers + r);
+  }
+  return ok;
 }
 
 // Solver kernels defined in pcg.cu, launched by both drivers.
@@ -143,6 +179,10 @@ __global__ void __launch_bounds__(256) pcg_update_kernel(int64_t n, const double
                                   PcgState* st, double* partials, const PeerView* pv);
 __global__ void __launch_bounds__(256) pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
                                      double* __restrict__ p, PcgState* st, double* history, const PeerView* pv);
+__global__ void __launch_bounds__(256, 3) pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__ u,
+                                const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s,
+                                double* __restrict__ x, double* __restrict__ r, PcgState* st, double* partials,
+                                double* history, const PeerView* pv);
 __global__ void __launch_bounds__(256) pcg_init_kernel(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
                                 double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, double tol,
                                 int max_iter, PcgState* st, double* partials);
@@ -152,5 +192,9 @@ int pcg_step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, 
                   const double* p, double* ap, int64_t p_row_offset, PcgState* st, double* partials,
                   cudaStream_t stream, const TmaPlan* plan, const PeerView* pv = nullptr);
 void pcg_match_carveout();
+// 0: classical PCG (3 kernels, 2 reductions per iteration); 1: single-reduction variant (2 kernels).
+// FEA_PCG_ALGO=0|1 overrides the automatic choice (see pcg.cu).
+constexpr int64_t kSingleReductionBelowDof = 3000000;
+int pcg_algorithm(int64_t n_dof, bool multi_gpu);
 
 }  // namespace fea

@@ -304,6 +304,7 @@ class P2PComm:
     exchange happen once, later solves only bump the epoch."""
 
     _cache: dict = {}
+    _warned = False
 
     @classmethod
     def get(cls, plan: SlabPlan, d: int, group=None) -> "P2PComm":
@@ -317,23 +318,45 @@ class P2PComm:
 
         lib = _lib.load()
         self.lib, self.plan, self.d, self.epoch = lib, plan, d, 0
-        nbytes = lib.fea_comm_bytes(plan.n_local * d)
-        own = ctypes.c_void_p()
-        _lib.check(lib.fea_comm_alloc(nbytes, ctypes.byref(own)), "fea_comm_alloc")
-        self.own = own.value
+        self.available, self.why = True, ""
+        self.own, self.ptrs, self.g_los = None, [], []
+
+        def agree(ok: bool, why: str) -> bool:
+            """Every rank must take the same path: all-reduce the local outcome."""
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag) == 0:
+                self.available, self.why = False, why if not ok else "a peer rank could not set up CUDA IPC"
+            return self.available
+
         handle = (ctypes.c_ubyte * 64)()
-        _lib.check(lib.fea_comm_ipc_export(self.own, ctypes.addressof(handle)), "fea_comm_ipc_export")
+        ok, why = True, ""
+        try:
+            nbytes = lib.fea_comm_bytes(plan.n_local * d)
+            own = ctypes.c_void_p()
+            _lib.check(lib.fea_comm_alloc(nbytes, ctypes.byref(own)), "fea_comm_alloc")
+            self.own = own.value
+            _lib.check(lib.fea_comm_ipc_export(self.own, ctypes.addressof(handle)), "fea_comm_ipc_export")
+        except Exception as exc:  # noqa: BLE001 -- reported, then every rank falls back together
+            ok, why = False, f"{type(exc).__name__}: {exc}"
+        if not agree(ok, why):
+            return
         infos = [None] * plan.world
         dist.all_gather_object(infos, (bytes(handle), plan.g_lo), group=group)
-        self.ptrs, self.g_los = [], [g for _, g in infos]
-        for r, (h, _) in enumerate(infos):
-            if r == plan.rank:
-                self.ptrs.append(self.own)
-                continue
-            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-            p = ctypes.c_void_p()
-            _lib.check(lib.fea_comm_ipc_open(ctypes.addressof(buf), ctypes.byref(p)), "fea_comm_ipc_open")
-            self.ptrs.append(p.value)
+        self.g_los = [g for _, g in infos]
+        try:
+            for r, (h, _) in enumerate(infos):
+                if r == plan.rank:
+                    self.ptrs.append(self.own)
+                    continue
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                p = ctypes.c_void_p()
+                _lib.check(lib.fea_comm_ipc_open(ctypes.addressof(buf), ctypes.byref(p)), "fea_comm_ipc_open")
+                self.ptrs.append(p.value)
+        except Exception as exc:  # noqa: BLE001
+            ok, why = False, f"{type(exc).__name__}: {exc}"
+        if not agree(ok, why):
+            return
         dist.barrier(group=group)  # every block is mapped everywhere before anyone writes
 
     def descriptor(self) -> "_lib.PeerComm":
@@ -415,8 +438,17 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
     ops = GpuOps(K, plan)
     if max_iter is None:
         max_iter = 10 * 3 * int(np.asarray(nodes).shape[0])
-    # NVLink peer-memory solver by default; FEA_DIST_COMM=nccl selects the torch.distributed loop
-    if plan.world > 1 and os.environ.get("FEA_DIST_COMM", "p2p") == "p2p":
+    # NVLink peer-memory solver by default; FEA_DIST_COMM=nccl selects the torch.distributed loop, which
+    # is also what every rank falls back to (together) when CUDA IPC cannot be set up between the ranks
+    use_p2p = plan.world > 1 and os.environ.get("FEA_DIST_COMM", "p2p") == "p2p"
+    if use_p2p and not P2PComm.get(plan, 3, group).available:
+        if plan.rank == 0 and not P2PComm._warned:
+            print(f"fea_b200.dist: peer-memory solver unavailable ({P2PComm.get(plan, 3, group).why}); "
+                  "using the NCCL driver", flush=True)
+            P2PComm._warned = True
+        use_p2p = False
+    SOLVER_USED["kind"] = "p2p" if use_p2p else ("nccl" if plan.world > 1 else "single")
+    if use_p2p:
         x, info = p2p_pcg(K, plan, b_owned, dinv_owned, tol, max_iter, group=group)
     else:
         x, info = distributed_pcg(ops, plan, 3, b_owned, dinv_owned, tol=tol, max_iter=max_iter, group=group)
@@ -430,6 +462,9 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
     mark("reactions", t)
     return x.reshape(-1, 3), reactions.reshape(-1, 3), info, K
 
+
+# which distributed solver the last solve_hex8_slab call used ("p2p" | "nccl" | "single")
+SOLVER_USED: dict = {"kind": None}
 
 # stage timings of solve_hex8_slab (ms, accumulated; each stage ends with a device synchronise) when
 # STAGE_PROFILE["enabled"] is set -- bench.py switches it on for ONE extra untimed step.
@@ -522,12 +557,12 @@ def bench_entry(args, A, b, tol, E, nu, measured_peaks, ClockSampler, cpu_sample
                        "free_dof": n_free, "elements": int(elements.shape[0]), "tol": tol,
                        "pcg_iterations": info.iterations, "rel_residual": info.rel_residual,
                        "preconditioner": "jacobi",
-                       "parallelism": (f"{world} z-slabs, NVLink peer-memory halo push + one-shot all-reduce "
-                                       "kernels inside the solver's CUDA graph (no NCCL per iteration)"
-                                       if os.environ.get("FEA_DIST_COMM", "p2p") == "p2p" else
+                       "parallelism": (f"{world} z-slabs, NVLink peer-memory exchange fused into the three PCG "
+                                       "kernels of the solver's CUDA graph (no NCCL per iteration)"
+                                       if SOLVER_USED["kind"] == "p2p" else
                                        f"{world} z-slabs, NCCL halo send/recv + all-reduced dots"),
                        "l2": "per-rank CSR slab larger than L2 for N <= 8; no flush"},
-            "roofline": {"kernel": "spmv_kernel<3> on the rank's slab (timed alone after the steps)", "bound": "hbm",
+            "roofline": {"kernel": "spmv_tma_kernel<3,2> on the rank's slab (timed alone after the steps)", "bound": "hbm",
                          "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak,
                          "traffic": None, "peak_source": peak_src, "aggregate_gb_per_s": float(agg),
                          "slowest_rank_ms": float(stats[0])},

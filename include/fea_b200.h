@@ -232,9 +232,11 @@ int fea_pcg_step_direction(int64_t n_dof, const double* dinv, const double* r, d
  *      Every rank allocates one communication block (header + its halo-extended p vector) with
  *      fea_comm_alloc, exports it with fea_comm_ipc_export, and maps its peers' blocks with
  *      fea_comm_ipc_open (CUDA IPC; the 64-byte handles travel through any host channel, e.g.
- *      torch.distributed.all_gather_object).  fea_pcg_solve_p2p then runs the whole iteration --
- *      halo push into the neighbours' memory, one-shot all-reduces of the dot products, the three
- *      solver kernels -- as one CUDA graph per 32 iterations, without NCCL.
+ *      torch.distributed.all_gather_object).  fea_pcg_solve_p2p then runs the iteration as one CUDA
+ *      graph per 32 iterations, without NCCL: the dot products are exchanged through the peers' slot
+ *      arrays and the halo rows of p are stored into the neighbours' memory from inside the three
+ *      solver kernels (3 launches per iteration; csrc/p2p.cu, csrc/pcg_common.cuh).  The last 512
+ *      bytes of the 4 KiB header of a block are reserved for the library (device copy of the view).
  * ---------------------------------------------------------------------------------------- */
 #define FEA_MAX_PEERS 8
 typedef struct {

@@ -231,8 +231,9 @@ def test_spmv_spmm_vs_scipy(mods):
     assert np.abs(K.matvec(core.to_device(t, torch.float64)).cpu().numpy()).max() < 1e-12 * np.abs(Kref.data).max()
 
 
-def test_pcg_vs_oracle(mods):
+def test_pcg_vs_oracle(mods, monkeypatch):
     core = mods["core"]
+    monkeypatch.setenv("FEA_PCG_ALGO", "0")  # the classical recurrence is the one the oracle states
     nodes, elements, cons, forces = fo.cantilever_case(20, 4)
     nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
     fixed = core._fixed_mask(cons, nodes.size)
@@ -262,6 +263,49 @@ def test_pcg_vs_oracle(mods):
     k = min(40, len(h), len(ho))
     assert np.allclose(h[:k], ho[:k], rtol=1e-6)
     assert np.all(u.cpu().numpy()[cons.ravel() != 0] == 0.0)
+
+
+def test_pcg_single_reduction_variant(mods, monkeypatch):
+    """FEA_PCG_ALGO=1 (Chronopoulos-Gear: 2 kernels, 1 reduction per iteration) against the classical
+    recurrence: same iterates in exact arithmetic -> same solution (1e-8), iteration count within a
+    few, residual history tracking; max_iter, zero right-hand side and history bookkeeping."""
+    core = mods["core"]
+    nodes, elements, cons, forces = fo.cantilever_case(20, 4)
+    # jittered interior nodes and a random load: on the symmetric uniform mesh the iteration count is
+    # decided by rounding noise (311 / 417 / 420 for three roundings of the same K, see
+    # test_pcg_vs_oracle); a generic mesh makes the two recurrences comparable iteration by iteration
+    rng = np.random.default_rng(3)
+    h = 0.1 / 4
+    nodes = nodes + rng.uniform(-0.15 * h, 0.15 * h, nodes.shape) * (nodes[:, 2:3] > 0)
+    forces = forces + 0.1 * np.abs(forces).max() * rng.standard_normal(forces.shape)
+    nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
+    K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, fixed=core._fixed_mask(cons, nodes.size))
+    b = core.to_device(forces, torch.float64).reshape(-1)
+    monkeypatch.setenv("FEA_PCG_ALGO", "0")
+    u0, i0 = core.pcg(K, b, tol=1e-12, history=True)
+    monkeypatch.setenv("FEA_PCG_ALGO", "1")
+    u1, i1 = core.pcg(K, b, tol=1e-12, history=True)
+    assert i1.status == 0 and i1.rel_residual <= 1e-12
+    assert abs(i1.iterations - i0.iterations) <= max(5, i0.iterations // 50)
+    assert rel(u1.cpu().numpy(), u0.cpu().numpy()) < U_RTOL
+    k = min(40, len(i0.history), len(i1.history))
+    assert np.allclose(i1.history[:k], i0.history[:k], rtol=1e-6)
+    assert len(i1.history) == i1.iterations and abs(i1.history[-1] - i1.rel_residual) < 1e-15
+    assert np.all(u1.cpu().numpy()[cons.ravel() != 0] == 0.0)
+    # iteration cap: exactly max_iter iterations, FEA_ERR_MAXITER
+    u2, i2 = core.pcg(K, b, tol=1e-12, max_iter=37, raise_on_failure=False)
+    assert i2.iterations == 37 and i2.status != 0
+    # the capped iterate equals the classical one after the same number of iterations
+    monkeypatch.setenv("FEA_PCG_ALGO", "0")
+    u3, i3 = core.pcg(K, b, tol=1e-12, max_iter=37, raise_on_failure=False)
+    assert i3.iterations == 37 and rel(u2.cpu().numpy(), u3.cpu().numpy()) < 1e-9
+    monkeypatch.setenv("FEA_PCG_ALGO", "1")
+    uz, iz = core.pcg(K, torch.zeros_like(b), tol=1e-12)
+    assert iz.status == 0 and iz.iterations == 0 and float(uz.abs().max()) == 0.0
+    # end to end through the reference-facing call
+    ud, _, _ = fo.solve_hex8(nodes, elements, cons, forces, method="direct")
+    u_api, f_api = mods["cubebeam"].solve(nodes, elements, cons, forces)
+    assert rel(u_api.ravel(), ud.ravel()) < U_RTOL
 
 
 def test_pcg_zero_rhs_and_singular(mods):
