@@ -495,6 +495,70 @@ def test_config4_assembly_properties(mods):
     assert float(x @ Kx) > 0
 
 
+def test_config2_full_size_properties(mods):
+    """BASELINE config 2 (Euler-Bernoulli, 100 k elements) assembled at full size: structural nnz of a
+    chain, rigid-body null space (uniform deflection; uniform rotation with the matching linear
+    deflection), symmetry, and the analytic tip deflection P L^3 / (3 EI) recovered from a moderately
+    sized cantilever (the 100 k solve itself is beyond FP64 conditioning)."""
+    core, EB = mods["core"], mods["eb"]
+    n = 100_000
+    elements, EI, Ls, cons, loads = EB.cantilever_case(n)
+    el = core.to_device(elements, torch.int32)
+    K = core.assemble_beam(core.to_device(EI, torch.float64), core.to_device(Ls, torch.float64), el, n + 1)
+    assert K.n_dof == 200_002 and K.nnz == 4 * (3 * (n + 1) - 2) == 1_200_004
+    scale = float(K.values.abs().max())
+    w = torch.zeros(K.n_dof, dtype=torch.float64, device="cuda")
+    w[0::2] = 1.0  # rigid translation
+    assert float(K.matvec(w).abs().max()) < 1e-9 * scale
+    xs = torch.arange(n + 1, dtype=torch.float64, device="cuda") * float(Ls[0])
+    rot = torch.zeros_like(w)
+    rot[0::2], rot[1::2] = xs, 1.0  # rigid rotation: w = x, theta = 1
+    assert float(K.matvec(rot).abs().max()) < 1e-9 * scale * float(rot.abs().max())
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(K.n_dof, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.randn(K.n_dof, dtype=torch.float64, device="cuda", generator=g)
+    assert abs(float(K.matvec(x) @ y - x @ K.matvec(y))) < 1e-10 * abs(float(K.matvec(x) @ y))
+    # analytic check where FP64 can carry it (cond ~ n^4): 50 Hermite elements are nodally exact for a tip load
+    e2, EI2, L2, c2, l2 = EB.cantilever_case(50)
+    u = EB.solve_beam(e2, EI2, L2, c2, l2)
+    tip = -1000.0 * 1.0**3 / (3 * 210e9 * 1e-6)
+    assert abs(np.asarray(u).reshape(-1, 2)[-1, 0] - tip) < 1e-6 * abs(tip)
+
+
+def test_config5_full_size_properties(mods):
+    """BASELINE config 5 (jittered lattice truss n = 93: 10,224,788 members, 2.4 M DOF) assembled at
+    full size: member and structural non-zero counts frozen in SURVEY.md §8(d), rigid translations in
+    the null space of the unconstrained K, symmetry and linearity of the 64-column SpMM, one batched
+    PCG chunk reducing every column's residual."""
+    core, T = mods["core"], mods["truss"]
+    nodes, members, k, cons, loads = T.lattice_truss(93, 64)
+    assert members.shape[0] == 10_224_788 and nodes.shape[0] == 804_357
+    nd, mem = core.to_device(nodes, torch.float64), core.to_device(members, torch.int32)
+    kd = core.to_device(k, torch.float64)
+    K = core.assemble_truss(nd, mem, kd)
+    assert K.n_dof == 2_413_071 and K.nnz == 191_285_397
+    scale = float(K.values.abs().max())
+    Tm = torch.zeros((K.n_dof, 4), dtype=torch.float64, device="cuda")
+    for c in range(3):
+        Tm[c::3, c] = 1.0
+    assert float(K.matmat(Tm).abs().max()) < 1e-11 * scale  # 4 columns: scalar path of the SpMM
+    B = core.to_device(loads, torch.float64)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    Y = torch.randn(B.shape, dtype=torch.float64, device="cuda", generator=g)
+    KB, KY = K.matmat(B), K.matmat(Y)
+    lhs, rhs = (KB * Y).sum(dim=0), (B * KY).sum(dim=0)
+    assert float(((lhs - rhs).abs() / lhs.abs()).max()) < 1e-9
+    Z = K.matmat(2.0 * B - 3.0 * Y)
+    assert float((Z - (2.0 * KB - 3.0 * KY)).abs().max()) < 1e-12 * float(KB.abs().max())
+    del KB, KY, Z, Y
+    Kc = core.assemble_truss(nd, mem, kd, fixed=core._fixed_mask(cons, nodes.size))
+    X, info = core.pcg_multi(Kc, B, tol=1e-12, max_iter=48, raise_on_failure=False)
+    R = B - Kc.matmat(X)
+    free = core._fixed_mask(cons, nodes.size) == 0
+    rel_res = R[free].norm(dim=0) / B[free].norm(dim=0)
+    assert info.iterations == 48 and float(rel_res.max()) < 0.5  # every column is converging
+
+
 def test_p2p_solver_single_rank(mods):
     """fea_pcg_solve_p2p with world = 1 (no peers): exercises the comm block API, the private
     stream / CUDA-graph driver and the p-in-comm-block layout on one GPU; must reproduce
