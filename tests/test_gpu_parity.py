@@ -436,6 +436,54 @@ def test_spmm_and_multi_rhs_wide_rows_and_odd_widths(mods):
         assert rel(U[free], lu.solve(X[free])) < U_RTOL
 
 
+def test_spmm_and_multi_rhs_other_block_sizes(mods):
+    """The SpMM / batched-PCG kernels at D = 2 (beam blocks) and D = 1 (plain DOF-level CSR), odd and
+    even RHS counts: the value-slab layout and the union gather are templated on D."""
+    import scipy.sparse.linalg as spla
+
+    from fea_b200 import _lib
+
+    core, EB = mods["core"], mods["eb"]
+    rng = np.random.default_rng(5)
+    n = 40
+    elements, EI, Ls, cons, loads = EB.cantilever_case(n)
+    EI = EI * rng.uniform(0.5, 1.5, n)
+    fixed = core._fixed_mask(cons, 2 * (n + 1))
+    K = core.assemble_beam(core.to_device(EI, torch.float64), core.to_device(Ls, torch.float64),
+                           core.to_device(elements, torch.int32), n + 1, fixed=fixed)
+    Kref = K.to_scipy()
+    free = fo.free_dofs(cons)
+    lu = spla.splu(Kref[free][:, free].tocsc())
+    for r in (1, 3, 8):
+        X = rng.standard_normal((K.n_dof, r))
+        Xd = core.to_device(X, torch.float64)
+        assert rel(K.matmat(Xd).cpu().numpy(), Kref @ X) < 1e-13
+        U, info = core.pcg_multi(K, Xd, tol=1e-12)
+        assert info.status == 0 and info.rel_residual <= 1e-12
+        assert rel(U.cpu().numpy()[free], lu.solve(X[free])) < 1e-5  # cond(K_ff) ~ 1e7
+    # D = 1: the hex8 matrix through its DOF-level arrays
+    nodes, els, _, _ = fo.cantilever_case(5, 3)
+    Kh = core.assemble_hex8(core.to_device(nodes, torch.float64), core.to_device(els, torch.int32), 1.0, 0.3)
+    Khref = Kh.to_scipy()
+    rowptr, colidx = Kh.pattern.csr(3)
+    for r in (2, 5):
+        X = rng.standard_normal((Kh.n_dof, r))
+        Xd = core.to_device(X, torch.float64)
+        Y = torch.empty_like(Xd)
+        rc = _lib.load().fea_spmm(Kh.n_dof, 1, rowptr.data_ptr(), colidx.data_ptr(), Kh.values.data_ptr(),
+                                  Xd.data_ptr(), Y.data_ptr(), r, None)
+        assert rc == 0 and rel(Y.cpu().numpy(), Khref @ X) < 1e-13
+    # D = 1 with short rows (<= 6 entries): the union-gather path instead of the wide-row path
+    rowptr, colidx = K.pattern.csr(2)
+    for r in (4, 7):
+        X = rng.standard_normal((K.n_dof, r))
+        Xd = core.to_device(X, torch.float64)
+        Y = torch.empty_like(Xd)
+        rc = _lib.load().fea_spmm(K.n_dof, 1, rowptr.data_ptr(), colidx.data_ptr(), K.values.data_ptr(),
+                                  Xd.data_ptr(), Y.data_ptr(), r, None)
+        assert rc == 0 and rel(Y.cpu().numpy(), Kref @ X) < 1e-13
+
+
 def test_mesh_extrude_device(mods):
     U, C = mods["utils"], mods["cubebeam"]
     n2, q2 = C.generate_quad_grid(5, 3, 0.3, 0.2)
