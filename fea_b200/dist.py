@@ -425,8 +425,13 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
     t = time.perf_counter()
     g_lo, g_hi = plan.g_lo, plan.g_hi
     nodes_d = core.to_device(np.ascontiguousarray(nodes[g_lo:g_hi]), torch.float64)
-    el_local = np.ascontiguousarray(elements[plan.element_ids] - g_lo)
-    elements_d = core.to_device(el_local, torch.int32)
+    ids = plan.element_ids
+    if ids.size and int(ids[-1]) - int(ids[0]) + 1 == ids.size:
+        # slabs of a layer-major mesh own a contiguous element range: a view, shifted on the device
+        el_view = np.ascontiguousarray(np.asarray(elements)[int(ids[0]):int(ids[-1]) + 1])
+        elements_d = (core.to_device(el_view, torch.int64) - g_lo).to(torch.int32)
+    else:
+        elements_d = core.to_device(np.ascontiguousarray(np.asarray(elements)[ids] - g_lo), torch.int32)
     fixed = core._fixed_mask(np.ascontiguousarray(np.asarray(constraints)[g_lo:g_hi]), 3 * plan.n_local)
     t = mark("slice_h2d", t)
     K = core.assemble_hex8(nodes_d, elements_d, E, nu, fixed=fixed)
