@@ -2,18 +2,29 @@
 """Benchmark of the hot path: hex8 cantilever assembled and solved to a 1e-12 recurrence residual.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A,b]
+    torchrun --nproc-per-node N bench.py --gpus N ...                      (N > 1, one rank per GPU)
 
 One "step" = one full pass of the hot path over the workload: symbolic pass + fused Ke/assembly +
 Jacobi-PCG to ||r|| <= 1e-12 ||b|| + reaction product.  Metric (BASELINE.json): solved DOF/s =
 free DOF / step time.  Workload (all N): BASELINE config "cubebeam hex8 cantilever 400x80x80"
-(7,892,883 DOF, 2,560,000 elements, structural nnz 627,797,529); N > 1 partitions the SAME
-mesh into z-slabs (strong scaling) with a halo exchange per SpMV and all-reduced dot products.
+(7,892,883 DOF, 2,560,000 elements, structural nnz 627,797,529); N > 1 partitions the SAME mesh
+into z-slabs (strong scaling): a halo exchange per SpMV and world sums of the dot products.
 
-Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event timed.  `e2e`: the
-reference-facing call `cubebeam.solve(nodes, elements, constraints, forces)` on pinned HOST arrays,
-host<->device copies inside the timed region.  `roofline`: the dominant kernel (PCG SpMV), timed
-live with CUDA events inside the timed steps.  `cpu_baseline`: the oracle (numpy/scipy port of the
-reference path) timed on this box's host cores on a bounded slab of the same mesh.
+Prints ONE JSON line (rank 0).
+  value      inputs resident in HBM (each rank's slab at N > 1), CUDA-event timed, max over ranks.
+  e2e        the reference-facing call cubebeam.solve(nodes, elements, constraints, forces) on HOST
+             arrays, host->device copies, gather and device->host copy of (displacements, forces)
+             inside the timed region; at N > 1 the same call is collective and rank 0 receives the
+             full host arrays (fea_b200/dist.py:solve_hex8).
+  roofline   the dominant kernel (PCG SpMV), timed live with CUDA events inside the timed solves;
+             `achieved` counts the bytes the node-block format has to move, the
+             scalar-CSR figure of SURVEY.md §8(d) is reported beside it under its own keys.
+  cpu_baseline / --impl reference
+             the CPU arm: oracle/fea_oracle_c.c (our C/OpenMP restatement of the reference
+             algorithm, the reference itself being single-threaded Python that cannot hold this
+             size) on ALL host cores, on the FULL mesh: pattern, Ke + assembly and reduction are
+             timed once at full size, the Jacobi-PCG is sampled (>= 500 iterations on the full
+             matrix with the driver's K = 20) and scaled to the iteration count of the full solve.
 """
 from __future__ import annotations
 
@@ -33,6 +44,7 @@ if ROOT not in sys.path:
 
 TOL = 1e-12
 E_HEX, NU_HEX = 10_000_000 * 6894.76, 0.3
+METRIC, UNIT = "hex8 beam solved DOF/s", "solved DOF/s"
 
 
 def parse_args():
@@ -45,7 +57,27 @@ def parse_args():
                     help="A,b: A element layers along z, b x b elements in the section")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=0,
+                    help="Jacobi-PCG iterations per CPU step (0: sized so that a step takes about 1.5 s, >= 25)")
+    ap.add_argument("--cpu-full-solve", action="store_true",
+                    help="--impl reference: also run the CPU Jacobi-PCG to convergence once (5-10 min at 400,80)")
     return ap.parse_args()
+
+
+def mesh_counts(A: int, b: int):
+    n1, n3 = b + 1, A + 1
+    return {"nodes": n1 * n1 * n3, "dof": 3 * n1 * n1 * n3, "free_dof": 3 * n1 * n1 * A, "elements": A * b * b,
+            "nnz": 9 * (3 * n1 - 2) ** 2 * (3 * n3 - 2)}
+
+
+def workload_config(A: int, b: int, world: int):
+    """The static description of the workload: identical in both arms (`--impl ours|reference`)."""
+    c = mesh_counts(A, b)
+    return {"workload": f"cubebeam hex8 cantilever {A}x{b}x{b}", "dof": c["dof"], "free_dof": c["free_dof"],
+            "elements": c["elements"], "nnz": c["nnz"], "tol": TOL, "preconditioner": "jacobi",
+            "parallelism": "single GPU" if world == 1 else f"{world} z-slabs of node layers, one rank per GPU",
+            "l2": "inputs larger than L2 (CSR values 5.0 GB over all ranks, >= 0.63 GB per rank at N <= 8, "
+                  "L2 126 MB); no flush"}
 
 
 def measured_peaks():
@@ -57,13 +89,20 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(workload: str):
+def committed_traffic(key: str):
     """dram bytes per SpMV launch from the committed `ncu --set full` capture, if there is one."""
     try:
         with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as fh:
-            return json.load(fh).get(workload)
+            return json.load(fh).get(key)
     except Exception:
         return None
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -112,124 +151,226 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle on a bounded slab of the same mesh, extrapolated to the full workload
+# CPU arm: the C/OpenMP oracle on all host cores, full-size mesh, sampled PCG
 # ----------------------------------------------------------------------------------------------
-def cpu_sample(A: int, b: int, iterations_full: int | None, slab_layers: int = 16, pcg_iters: int = 20):
-    """CPU arm on `slab_layers` element layers of the b x b section, scaled to the workload
-    (assembly linearly in elements, PCG linearly in nnz x iterations).
+def recorded_iterations(A: int, b: int):
+    """Iterations the ORACLE's Jacobi-PCG needs on this workload, from the committed fixtures
+    (oracle/make_golden_large.py); None for a workload without a fixture."""
+    name = {(400, 80): "oracle_config4.npz", (100, 20): "oracle_config3.npz"}.get((A, b))
+    if name is None:
+        return None
+    try:
+        return int(np.load(os.path.join(ROOT, "tests", "golden", name))["iterations"])
+    except Exception:
+        return None
 
-    Headline figure: oracle/fea_oracle_c.c -- OUR OWN C/OpenMP port of the reference algorithm
-    (utils.py:127-239 + cubebeam.py:79-108 with the sparse Jacobi-PCG) on all host threads.  It is
-    a port written for this bench with straightforward parallel loops (no cache blocking, no NUMA
-    pinning), not the reference's code: the reference is single-threaded Python and cannot hold
-    this size.  The single-core numpy/scipy oracle, which is closest to what the reference itself
-    executes, is timed beside it (`numpy_1core_*`) so that both comparisons are on the line."""
-    from oracle import c_oracle as co
-    from oracle import fea_oracle as fo
 
-    layers = min(slab_layers, A)
-    nodes, elements, cons, forces = fo.cantilever_case(layers, b, beam_length=layers / A)
-    n_elem_full = A * b * b
-    n1, n3 = b + 1, A + 1
-    nnz_full = 9 * (3 * n1 - 2) ** 2 * (3 * n3 - 2)
-    free_full = 3 * n1 * n1 * A
-    if iterations_full is None:
-        iterations_full = int(21.3 * A)  # SURVEY.md H1: ~linear in the long dimension
-    free = fo.free_dofs(cons)
-    ff = forces.flatten()[free]
+class CpuArm:
+    """oracle/fea_oracle_c.c on the host: our C/OpenMP restatement of utils.py:127-239 (dense
+    B^T C B Ke in the reference's order) + cubebeam.py:79-108 (scatter, reduction, Jacobi-PCG in place
+    of np.linalg.solve).  Plain parallel loops, not cache-blocked or NUMA-pinned.  The thread count is
+    pinned to the host's cores explicitly: torchrun exports OMP_NUM_THREADS=1 to every rank."""
 
-    # --- C / OpenMP port, all host threads
-    cores = co.threads()
-    t0 = time.perf_counter()
-    pattern = co.dof_pattern(elements, nodes.shape[0], 3)
-    t1 = time.perf_counter()
-    K = co.assemble_hex8(nodes, elements, E_HEX, NU_HEX, pattern=pattern)
-    t2 = time.perf_counter()
-    Kff = K[free][:, free].tocsr()
-    t3 = time.perf_counter()
-    co.jacobi_pcg(Kff, ff, tol=0.0, maxiter=5)  # thread pool / page warm-up
-    t4 = time.perf_counter()
-    c_iters = 10 * pcg_iters
-    co.jacobi_pcg(Kff, ff, tol=0.0, maxiter=c_iters)
-    t5 = time.perf_counter()
-    c_asm = ((t2 - t0) + (t3 - t2)) * n_elem_full / elements.shape[0]
-    c_it = (t5 - t4) / c_iters * nnz_full / Kff.nnz
-    c_total = c_asm + c_it * iterations_full
+    def __init__(self, A: int, b: int):
+        from oracle import c_oracle as co
+        from oracle import fea_oracle as fo
 
-    # --- numpy / scipy oracle, one core (closest to the reference's own execution)
-    s0 = time.perf_counter()
-    Ke = fo.hex8_ke_batched(nodes, elements, E_HEX, NU_HEX)
-    s1 = time.perf_counter()
-    Kn = fo.assemble_csr(elements, Ke, nodes.shape[0], 3)
-    Knff = Kn[free][:, free].tocsr()
-    s2 = time.perf_counter()
-    del Ke
-    fo.jacobi_pcg(Knff, ff, tol=0.0, maxiter=pcg_iters)
-    s3 = time.perf_counter()
-    n_asm = (s2 - s0) * n_elem_full / elements.shape[0]
-    n_it = (s3 - s2) / pcg_iters * nnz_full / Knff.nnz
-    n_total = n_asm + n_it * iterations_full
+        self.A, self.b, self.co, self.fo = A, b, co, fo
+        self.cores = co.set_threads(host_cores())
+        self.counts = mesh_counts(A, b)
+        self.setup_s = {}
 
-    return {
-        "value": free_full / c_total,
-        "unit": "solved DOF/s",
-        "cores": cores,
-        "kind": "port",
-        "sample": (f"OUR C/OpenMP port of the reference algorithm (oracle/fea_oracle_c.c; plain parallel loops, not "
-                   f"cache-blocked or NUMA-pinned; the reference itself is single-threaded Python and cannot hold this "
-                   f"size) on {cores} threads, {layers}x{b}x{b} slab of the workload ({elements.shape[0]} elements, "
-                   f"nnz {Kff.nnz}): pattern {t1 - t0:.2f}s + Ke/assembly {t2 - t1:.2f}s + reduce {t3 - t2:.2f}s + "
-                   f"{c_iters} Jacobi-PCG iterations {t5 - t4:.2f}s; extrapolated linearly to {n_elem_full} elements "
-                   f"and {iterations_full} iterations x nnz {nnz_full} (= {c_total:.0f}s).  Beside it, the numpy/scipy "
-                   f"oracle on 1 core (what the reference's own code path amounts to): {n_total:.0f}s"),
-        "assembly_elem_per_s": elements.shape[0] / (t3 - t0),
-        "spmv_gb_per_s": (12 * Kff.nnz + 20 * Kff.shape[0]) / ((t5 - t4) / c_iters) / 1e9,
-        "numpy_1core_value": free_full / n_total,
-        "numpy_1core_ke_elem_per_s": elements.shape[0] / (s1 - s0),
-        "numpy_1core_assembly_elem_per_s": elements.shape[0] / (s2 - s0),
-        "numpy_1core_spmv_gb_per_s": (12 * Knff.nnz + 20 * Knff.shape[0]) / ((s3 - s2) / pcg_iters) / 1e9,
-        "seconds": (t5 - t0) + (s3 - s0),
-    }
+    def setup(self):
+        """Pattern, Ke + assembly and constraint reduction on the FULL mesh, each timed once."""
+        co, fo = self.co, self.fo
+        nodes, elements, cons, forces = fo.cantilever_case(self.A, self.b)  # host mesh, like the GPU arm's inputs
+        t0 = time.perf_counter()
+        pattern = co.dof_pattern(elements, nodes.shape[0], 3)
+        t1 = time.perf_counter()
+        K = co.assemble_hex8(nodes, elements, E_HEX, NU_HEX, pattern=pattern)
+        t2 = time.perf_counter()
+        free = fo.free_dofs(cons)
+        self.Kff = co.reduce_csr(K, free)
+        self.ff = forces.flatten()[free]
+        t3 = time.perf_counter()
+        del K, pattern
+        self.setup_s = {"pattern": t1 - t0, "ke_assembly": t2 - t1, "reduce": t3 - t2}
+        self.assembly_s = t3 - t0
+        co.jacobi_pcg(self.Kff, self.ff, tol=0.0, maxiter=3)  # thread pool / page warm-up
+        t4 = time.perf_counter()
+        co.jacobi_pcg(self.Kff, self.ff, tol=0.0, maxiter=5)
+        self.probe_iter_s = (time.perf_counter() - t4) / 5
+
+    def iters_per_step(self, requested: int) -> int:
+        if requested > 0:
+            return requested
+        return int(min(200, max(25, round(1.5 / max(self.probe_iter_s, 1e-6)))))
+
+    def step(self, iters: int) -> float:
+        """`iters` Jacobi-PCG iterations on the full reduced matrix (every iteration costs the same:
+        one SpMV + the vector updates), seconds."""
+        t0 = time.perf_counter()
+        self.co.jacobi_pcg(self.Kff, self.ff, tol=0.0, maxiter=iters)
+        return time.perf_counter() - t0
+
+    def full_solve(self):
+        t0 = time.perf_counter()
+        _, it, rel = self.co.jacobi_pcg(self.Kff, self.ff, tol=TOL)
+        return time.perf_counter() - t0, it, rel
+
+    def numpy_1core(self, iterations_full: int, layers: int = 8, pcg_iters: int = 20):
+        """The numpy/scipy oracle on one core -- closest to what the reference itself executes --
+        on a `layers`-layer slab, scaled linearly (assembly in elements, PCG in nnz x iterations)."""
+        fo = self.fo
+        layers = min(layers, self.A)
+        nodes, elements, cons, forces = fo.cantilever_case(layers, self.b, beam_length=layers / self.A)
+        free = fo.free_dofs(cons)
+        s0 = time.perf_counter()
+        Ke = fo.hex8_ke_batched(nodes, elements, E_HEX, NU_HEX)
+        Kn = fo.assemble_csr(elements, Ke, nodes.shape[0], 3)
+        Knff = Kn[free][:, free].tocsr()
+        s1 = time.perf_counter()
+        del Ke
+        fo.jacobi_pcg(Knff, forces.flatten()[free], tol=0.0, maxiter=pcg_iters)
+        s2 = time.perf_counter()
+        total = ((s1 - s0) * self.counts["elements"] / elements.shape[0]
+                 + (s2 - s1) / pcg_iters * self.counts["nnz"] / Knff.nnz * iterations_full)
+        return self.counts["free_dof"] / total
+
+    def summary(self, step_s: float, iters: int, steps_timed: int, iterations_full: int, iterations_source: str):
+        iter_s = step_s / iters
+        total = self.assembly_s + iter_s * iterations_full
+        s = self.setup_s
+        return {
+            "value": self.counts["free_dof"] / total, "unit": UNIT, "cores": self.cores, "kind": "port",
+            "sample": (f"oracle/fea_oracle_c.c (OUR C/OpenMP port of the reference algorithm; the reference itself is "
+                       f"single-threaded Python whose dense solve() cannot hold this size) on {self.cores} host threads, "
+                       f"FULL {self.A}x{self.b}x{self.b} mesh: pattern {s['pattern']:.2f}s + Ke/assembly "
+                       f"{s['ke_assembly']:.2f}s + reduction {s['reduce']:.2f}s measured once at full size; Jacobi-PCG "
+                       f"sampled on the full reduced matrix, {steps_timed} x {iters} iterations at "
+                       f"{iter_s * 1e3:.1f} ms/iteration, scaled to the {iterations_full} iterations of the full solve "
+                       f"({iterations_source}) = {total:.0f}s per solve"),
+            "assembly_elem_per_s": self.counts["elements"] / self.assembly_s,
+            "spmv_gb_per_s_csr": (12 * self.Kff.nnz + 20 * self.Kff.shape[0]) / iter_s / 1e9,
+            "ms_per_iteration": iter_s * 1e3, "iterations_full": iterations_full, "seconds_per_solve": total,
+        }
 
 
 def run_reference(args, A, b):
-    """--impl reference: the CPU arm.  The reference is pure Python and its dense solve() cannot hold
-    this workload (cubebeam.py:80: 498 TB), so the arm times OUR C/OpenMP port of its algorithm on all
-    host threads (kind "port", see cpu_sample); the 1-core numpy figure rides along in cpu_baseline."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the CPU arm on rank 0 (other ranks exit).  `ms_per_step` is the measured time of
+    one step = one bounded sample of the solve (cpu_iters PCG iterations on the full matrix); `value` is
+    free DOF / (full-size assembly, measured once + the full solve's iteration count x measured time per
+    iteration)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    n1 = b + 1
-    free_full = 3 * n1 * n1 * A
-    vals = []
-    sample = None
-    for i in range(args.warmup + args.steps):
-        sample = cpu_sample(A, b, None, slab_layers=8 if i < args.warmup else 16)
-        if i >= args.warmup:
-            vals.append(sample["value"])
-    value = float(np.mean(vals))
+    arm = CpuArm(A, b)
+    arm.setup()
+    iters = arm.iters_per_step(args.cpu_iters)
+    for _ in range(args.warmup):
+        arm.step(min(iters, 5))
+    secs = [arm.step(iters) for _ in range(max(args.steps, 1))]
+    step_s = float(np.mean(secs))
+    it_full = recorded_iterations(A, b)
+    src = "recorded by the oracle's own full solve, tests/golden"
+    if it_full is None:
+        it_full, src = int(21.3 * A), "estimated 21.3 x A, SURVEY.md H1"
+    cpu = arm.summary(step_s, iters, len(secs), it_full, src)
+    if args.cpu_full_solve:
+        t, it, rel = arm.full_solve()
+        cpu["full_solve_measured"] = {"seconds": t + arm.assembly_s, "pcg_seconds": t, "iterations": it, "rel_residual": rel}
+    cpu["numpy_1core_value"] = arm.numpy_1core(it_full)
     line = {
-        "impl": "reference", "metric": "hex8 beam solved DOF/s", "value": value, "unit": "solved DOF/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": free_full / value * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cubebeam hex8 cantilever {A}x{b}x{b}", "tol": TOL,
-                   "note": "our C/OpenMP port of the reference algorithm on a bounded slab, all host threads, "
-                           "extrapolated (see cpu_baseline.sample); not the reference's own code"},
-        "cpu_baseline": {k: sample[k] for k in ("value", "unit", "cores", "kind", "sample", "numpy_1core_value")},
-        "e2e": {"value": value, "unit": "solved DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(A, b, args.gpus),
+        "step_definition": (f"one step = {iters} Jacobi-PCG iterations on the full reduced matrix (a bounded sample of "
+                            f"the solve); value = free DOF / seconds_per_solve, see cpu_baseline.sample"),
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    line["cpu_baseline"]["value"] = value
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+class SingleGpu:
+    """Device-resident inputs on one GPU; step = symbolic + assembly + PCG + reactions."""
+
+    def __init__(self, mesh, torch, core):
+        nodes, elements, constraints, forces = mesh
+        self.torch, self.core = torch, core
+        self.nodes_d = core.to_device(nodes, torch.float64)
+        self.elements_d = core.to_device(elements, torch.int32)
+        self.fixed_d = core._fixed_mask(constraints, nodes.size)
+        self.loads_d = core.to_device(forces, torch.float64).reshape(-1)
+        self.n_nodes = nodes.shape[0]
+        self.K = self.info = None
+
+    def step(self):
+        core = self.core
+        pat = core.symbolic(self.elements_d, self.n_nodes)
+        self.K = core.assemble_hex8(self.nodes_d, self.elements_d, E_HEX, NU_HEX, pattern=pat, fixed=self.fixed_d)
+        _, _, self.info = core.solve_system(self.K, self.loads_d, tol=TOL)
+
+    def owned_format_bytes(self):
+        nnz, n = self.K.nnz, self.K.n_dof
+        return 8 * nnz + 4 * (nnz // 9) + 4 * (self.n_nodes + 1) + 16 * n, 12 * nnz + 20 * n
+
+    def stage_times(self):
+        torch, core = self.torch, self.core
+
+        def timed(fn):
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            out = fn()
+            c.record()
+            torch.cuda.synchronize()
+            return out, a.elapsed_time(c)
+
+        pat, ms_sym = timed(lambda: core.symbolic(self.elements_d, self.n_nodes))
+        _, ms_num = timed(lambda: core.assemble_hex8(self.nodes_d, self.elements_d, E_HEX, NU_HEX, pattern=pat,
+                                                     fixed=self.fixed_d))
+        return {"symbolic": ms_sym, "numeric_assembly": ms_num}
+
+
+class Slabs:
+    """N > 1: each rank's slab resident on its GPU; step = symbolic + assembly + distributed PCG
+    + reactions (fea_b200/dist.py:solve_slab)."""
+
+    def __init__(self, mesh, torch, fdist, rank, world):
+        nodes, elements, constraints, forces = mesh
+        self.torch, self.fdist = torch, fdist
+        self.cuts = fdist.default_cuts(nodes.shape[0], world)
+        self.plan = fdist.plan_slab(elements, self.cuts, rank)
+        self.inp = fdist.upload_slab(nodes, elements, constraints, forces, self.plan)
+        self.max_rank_dof = 3 * int(np.diff(self.cuts).max())
+        self.K = self.info = None
+
+    def step(self):
+        _, _, self.info, self.K = self.fdist.solve_slab(self.inp, E_HEX, NU_HEX, tol=TOL,
+                                                         max_rank_dof=self.max_rank_dof)
+
+    def owned_format_bytes(self):
+        pl, rp = self.plan, self.K.pattern.node_rowptr
+        blocks = int(rp[pl.offset + pl.n_owned] - rp[pl.offset])
+        nnz, n = 9 * blocks, 3 * pl.n_owned
+        return 8 * nnz + 4 * blocks + 4 * (pl.n_owned + 1) + 16 * n, 12 * nnz + 20 * n
+
+    def stage_times(self):
+        return {}
+
+
 def run_ours(args, A, b):
+    import ctypes
+
     import torch
 
-    from fea_b200 import _lib, core, cubebeam, model
+    from fea_b200 import _lib, core, cubebeam
+    from fea_b200 import dist as fdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -237,131 +378,158 @@ def run_ours(args, A, b):
     torch.cuda.set_device(local_rank)
     lib = _lib.load()
     if world > 1:
-        from fea_b200 import dist as fdist
+        import torch.distributed as dist
 
-        return fdist.bench_entry(args, A, b, TOL, E_HEX, NU_HEX, measured_peaks, ClockSampler, cpu_sample)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    workload = f"cubebeam hex8 cantilever {A}x{b}x{b}"
-    nodes, elements, constraints, forces = cubebeam.cantilever_case(A, b)
-    n_nodes, n_dof = nodes.shape[0], nodes.size
-    n_free = int((constraints == 0).sum())
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    # pinned host copies (e2e inputs) and device-resident copies (kernel-path inputs)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    nodes_h, elements_h, cons_h, forces_h = pin(nodes), pin(elements), pin(constraints), pin(forces)
-    nodes_d = nodes_h.cuda()
-    elements_d = elements_h.cuda().to(torch.int32)
-    fixed_d = (cons_h.cuda().reshape(-1) != 0).to(torch.uint8)
-    loads_d = forces_h.cuda().reshape(-1)
-    torch.cuda.synchronize()
+    def world_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
 
-    state = {}
+    def world_sum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t)
 
-    def step_device():
-        pat = core.symbolic(elements_d, n_nodes)
-        K = core.assemble_hex8(nodes_d, elements_d, E_HEX, NU_HEX, pattern=pat, fixed=fixed_d)
-        u, reactions, info = core.solve_system(K, loads_d, tol=TOL)
-        state.update(K=K, info=info, u=u, reactions=reactions)
+    counts = mesh_counts(A, b)
+    mesh = cubebeam.cantilever_case(A, b)
+    n_free = counts["free_dof"]
+    runner = SingleGpu(mesh, torch, core) if world == 1 else Slabs(mesh, torch, fdist, rank, world)
 
+    # ---- device-resident steps: `value`
     for _ in range(args.warmup):
-        step_device()
-    torch.cuda.synchronize()
+        runner.step()
+    barrier()
     lib.fea_profile_enable(1)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     ev0.record()
     for _ in range(args.steps):
-        step_device()
+        runner.step()
     ev1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    prof = (4 * __import__("ctypes").c_double)()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = world_max(ev0.elapsed_time(ev1) / args.steps)
+    prof = (4 * ctypes.c_double)()
     lib.fea_profile_read(prof)
     lib.fea_profile_enable(0)
-    ms_per_step = ev0.elapsed_time(ev1) / args.steps
     value = n_free / (ms_per_step / 1e3)
-    K, info = state["K"], state["info"]
-    nnz = K.nnz
-    launches = int(prof[0]) // max(args.steps, 1)
-    spmv_ms = prof[2] / max(prof[1], 1.0)
+    info = runner.info
+    launches = int(world_sum(float(prof[0]))) // max(args.steps, 1)
+    spmv_ms = prof[2] / max(prof[1], 1.0)          # this rank's PCG SpMV, sampled inside the timed solves
+    fmt_bytes, csr_bytes = runner.owned_format_bytes()
 
-    # stage timings (single extra pass, CUDA events): symbolic / numeric assembly / solve
-    def timed(fn):
-        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record()
-        out = fn()
-        c.record()
-        torch.cuda.synchronize()
-        return out, a.elapsed_time(c)
-
-    pat, ms_sym = timed(lambda: core.symbolic(elements_d, n_nodes))
-    Kt, ms_num = timed(lambda: core.assemble_hex8(nodes_d, elements_d, E_HEX, NU_HEX, pattern=pat, fixed=fixed_d))
-    _, ms_scatter = timed(lambda: _scatter(lib, nodes_d, elements_d, pat, torch))
-    del Kt
-
+    # ---- roofline of the dominant kernel: format bytes of this rank's rows / its own launch time
     hbm_peak, peak_src = measured_peaks()
-    alg_bytes = 12 * nnz + 20 * n_dof
-    moved_bytes = 8 * nnz + 4 * (nnz // 9) + 4 * (n_nodes + 1) + 16 * n_dof
-    achieved = alg_bytes / (spmv_ms / 1e3) / 1e9 if spmv_ms > 0 else None
+    mine = fmt_bytes / (spmv_ms / 1e3) / 1e9 if spmv_ms > 0 else 0.0
+    achieved = world_sum(mine) / world           # mean over ranks of the per-GPU figure
+    slowest_ms = world_max(spmv_ms)
+    csr_equiv = world_sum(csr_bytes / (spmv_ms / 1e3) / 1e9 if spmv_ms > 0 else 0.0) / world
+    traffic_key = f"{A}x{b}x{b}/N{world}"
     roofline = {
-        "kernel": "pcg_spmv_tma_kernel<3,2> (ap = K p fused with p.ap)", "bound": "hbm",
-        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
-        "traffic": committed_traffic(workload), "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": spmv_ms, "launches_timed": int(prof[1]),
-        "format_bytes_per_launch": moved_bytes,
-        "frac_of_format_bytes": moved_bytes / (spmv_ms / 1e3) / 1e9 / hbm_peak if spmv_ms > 0 else None,
-        "spmv_share_of_step": spmv_ms * info.iterations / ms_per_step if ms_per_step > 0 else None,
+        "kernel": ("pcg_spmv_tma_kernel<3,2> (ap = K p fused with p.ap"
+                   + (", halo-gated face tiles" if world > 1 else "") + ")"),
+        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "traffic": committed_traffic(traffic_key), "peak_source": peak_src,
+        "bytes_counted": "node-block CSR format bytes of the rank's rows: 8 B/value + 4 B per 3x3 block + 4 B per "
+                         "node rowptr + 16 B per DOF (x read, y written); per GPU, mean over ranks",
+        "format_bytes_per_launch": fmt_bytes, "avg_launch_ms": spmv_ms, "slowest_rank_avg_launch_ms": slowest_ms,
+        "launches_timed": int(prof[1]),
+        "csr_equivalent_gb_per_s": csr_equiv, "csr_equivalent_frac": csr_equiv / hbm_peak,
+        "csr_equivalent_bytes_per_launch": csr_bytes,
+        "spmv_share_of_step": slowest_ms * info.iterations / ms_per_step if ms_per_step > 0 else None,
     }
 
-    # end to end through the reference-facing API with pinned host buffers
+    # ---- where a step goes (one extra untimed pass)
+    stages = runner.stage_times()
+    iter_us = None
+    if world == 1:
+        iter_us = (ms_per_step - stages["symbolic"] - stages["numeric_assembly"]) / max(info.iterations, 1) * 1e3
+        stages["pcg_iteration_avg_us"] = iter_us
+        stages["pcg_spmv_avg_us"] = spmv_ms * 1e3
+    assembly_rates = None
+    if world == 1:
+        assembly_rates = {"symbolic": counts["elements"] / (stages["symbolic"] / 1e3),
+                          "numeric_incl_ke": counts["elements"] / (stages["numeric_assembly"] / 1e3)}
+
+    # ---- end to end through the reference-facing API with host buffers
     e2e = None
     if not args.no_e2e:
-        arrays = (nodes_h.numpy(), elements_h.numpy(), cons_h.numpy(), forces_h.numpy())
-        cubebeam.solve(*arrays)  # warm-up
-        torch.cuda.synchronize()
-        k_e2e = min(args.steps, 3)
+        pin = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()) if world == 1 else (lambda a: a)
+        arrays = tuple(pin(a) for a in mesh)
+        cubebeam.solve(*arrays)  # warm-up (IPC set-up, caches)
+        k_e2e = min(max(args.steps, 1), 3)
+        barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
             u_h, f_h = cubebeam.solve(*arrays)
-        torch.cuda.synchronize()
-        t_e2e = (time.perf_counter() - t0) / k_e2e
-        e2e = {"value": n_free / t_e2e, "unit": "solved DOF/s",
-               "h2d_bytes_per_step": int(sum(a.nbytes for a in arrays)),
-               "d2h_bytes_per_step": int(u_h.nbytes + f_h.nbytes), "ms_per_step": t_e2e * 1e3, "steps": k_e2e,
-               "api": "fea_b200.cubebeam.solve(nodes, elements, constraints, forces) on pinned numpy arrays"}
+        barrier()
+        t_e2e = world_max((time.perf_counter() - t0) / k_e2e)
+        if world == 1:
+            h2d = int(sum(a.nbytes for a in arrays))
+        else:
+            h2d = int(world_sum(float(runner.inp.h2d_bytes)))
+        d2h = int(world_sum(float(u_h.nbytes + f_h.nbytes) if u_h is not None else 0.0))
+        e2e = {"value": n_free / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": t_e2e * 1e3, "steps": k_e2e,
+               "api": "fea_b200.cubebeam.solve(nodes, elements, constraints, forces): host numpy arrays in, host "
+                      "(displacements, forces) out" + ("" if world == 1 else
+                                                       " on rank 0 (collective call; every rank copies its slab up, "
+                                                       "rank 0 gathers over NVLink and copies the result down)")}
+        if world > 1:
+            fdist.STAGE_PROFILE.clear()
+            fdist.STAGE_PROFILE["enabled"] = True
+            barrier()
+            cubebeam.solve(*arrays)
+            fdist.STAGE_PROFILE["enabled"] = False
+            stages = {k: round(v, 3) for k, v in fdist.STAGE_PROFILE.items() if k != "enabled"}
+            if "pcg" in stages:
+                stages["pcg_iteration_avg_us"] = stages["pcg"] / max(info.iterations, 1) * 1e3
+            stages["pcg_spmv_avg_us_slowest_rank"] = slowest_ms * 1e3
 
     cpu = None
-    if not args.no_cpu_baseline:
-        cpu = cpu_sample(A, b, info.iterations)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(A, b)
+        arm.setup()
+        iters = args.cpu_iters or int(min(400, max(50, round(8.0 / max(arm.probe_iter_s, 1e-6)))))
+        cpu = arm.summary(arm.step(iters), iters, 1, info.iterations, "the count of the GPU solve in this run")
+        cpu["numpy_1core_value"] = arm.numpy_1core(info.iterations)
 
-    line = {
-        "metric": "hex8 beam solved DOF/s", "value": value, "unit": "solved DOF/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "dof": n_dof, "free_dof": n_free, "elements": int(elements.shape[0]),
-                   "nnz": nnz, "tol": TOL, "pcg_iterations": info.iterations, "rel_residual": info.rel_residual,
-                   "preconditioner": "jacobi", "parallelism": "single GPU",
-                   "l2": "inputs larger than L2 (CSR values 5.0 GB >> 126 MB), no flush needed"},
-        "stages_ms": {"symbolic": ms_sym, "numeric_assembly_gather": ms_num, "numeric_assembly_scatter_atomics": ms_scatter,
-                      "pcg_iteration_avg": (ms_per_step - ms_sym - ms_num) / max(info.iterations, 1)},
-        "assembly_elem_per_s": {"symbolic": elements.shape[0] / (ms_sym / 1e3),
-                                "numeric_incl_ke": elements.shape[0] / (ms_num / 1e3)},
-        "spmv_gb_per_s": achieved,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
-    }
-    print(json.dumps(line))
-
-
-def _scatter(lib, nodes_d, elements_d, pat, torch):
-    vals = torch.zeros(9 * pat.nnz_blocks, dtype=torch.float64, device=nodes_d.device)
-    st = torch.zeros(2, dtype=torch.int32, device=nodes_d.device)
-    lib.fea_assemble_hex8_scatter(nodes_d.data_ptr(), elements_d.data_ptr(), elements_d.shape[0], E_HEX, NU_HEX,
-                                  pat.node_rowptr.data_ptr(), pat.node_colidx.data_ptr(), vals.data_ptr(),
-                                  st.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    return vals
+    if rank == 0:
+        cfg = workload_config(A, b, world)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "solve": {"pcg_iterations": info.iterations, "rel_residual": info.rel_residual,
+                      "solver": ("fea_pcg_solve" if world == 1 else
+                                 {"p2p": "fea_pcg_solve_p2p (NVLink peer-memory exchange fused into the solver kernels, "
+                                         "no NCCL per iteration)",
+                                  "nccl": "torch.distributed driver (NCCL halo send/recv + all-reduced dots)"}
+                                 .get(fdist.SOLVER_USED["kind"], "?"))},
+            "stages_ms" if world == 1 else "stages_ms_rank0": stages,
+            "assembly_elem_per_s": assembly_rates,
+            "spmv_gb_per_s": achieved,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -46,6 +46,7 @@ class PcgResult(ctypes.Structure):
 
 
 FEA_ERR_PEER = 8
+FEA_ERR_STAGNATION = 9
 MAX_PEERS = 8
 
 
@@ -59,6 +60,9 @@ class PeerComm(ctypes.Structure):
         ("send_lower_first", c_int64), ("send_lower_count", c_int64), ("send_lower_dst", c_int64),
         ("send_upper_first", c_int64), ("send_upper_count", c_int64), ("send_upper_dst", c_int64),
         ("epoch", c_int64),
+        ("boundary_lower_nodes", c_int64), ("boundary_upper_nodes", c_int64),
+        ("algo", c_int32), ("reserved", c_int32),
+        ("max_rank_dof", c_int64),
     ]
 
 
@@ -92,13 +96,14 @@ PROTOTYPES = {
     "fea_pcg_step_spmv": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, c_int64, P, P, P]),
     "fea_pcg_step_update": (c_int32, [c_int64, P, P, P, P, P, P, P, P]),
     "fea_pcg_step_direction": (c_int32, [c_int64, P, P, P, P, P, P]),
+    "fea_slab_scan": (c_int32, [P, c_int32, c_int64, c_int32, P, c_int32, P]),
     "fea_comm_bytes": (c_size_t, [c_int64]),
     "fea_comm_alloc": (c_int32, [c_size_t, ctypes.POINTER(c_void_p)]),
     "fea_comm_free": (c_int32, [P]),
     "fea_comm_ipc_export": (c_int32, [P, P]),
     "fea_comm_ipc_open": (c_int32, [P, ctypes.POINTER(c_void_p)]),
     "fea_comm_ipc_close": (c_int32, [P]),
-    "fea_pcg_solve_p2p": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, P, c_double, c_int32, P, c_size_t,
+    "fea_pcg_solve_p2p": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, P, c_double, c_int32, P, c_size_t, P,
                                     ctypes.POINTER(PeerComm), ctypes.POINTER(PcgResult), P]),
     "fea_pcg_multi_workspace": (c_size_t, [c_int64, c_int32]),
     "fea_pcg_solve_multi": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, c_int32, c_double, c_int32, P, c_size_t,
@@ -167,4 +172,9 @@ def raise_for_status(status_host: np.ndarray) -> None:
         raise np.linalg.LinAlgError("Singular matrix")  # what np.linalg.solve raises, cubebeam.py:98
     if code == FEA_ERR_MAXITER:
         raise np.linalg.LinAlgError("PCG did not converge within max_iter")
+    if code == FEA_ERR_STAGNATION:  # under-constrained body: the reduced K is singular (cubebeam.py:98)
+        raise np.linalg.LinAlgError("Singular matrix (PCG residual stopped improving)")
+    if code == FEA_ERR_PEER:
+        raise FeaLibraryError("multi-GPU solve: a peer rank never delivered its halo / partial sum, "
+                              "or the ranks disagree on the recurrence")
     raise FeaLibraryError(f"device status {code}")

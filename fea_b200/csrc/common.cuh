@@ -100,6 +100,32 @@ __device__ __forceinline__ void raise_status(int32_t* status, int code, int inde
   atomicMax(&status[1], 0x7fffffff - index);
 }
 
+// System-scope release / acquire on 64-bit flags: the cross-GPU tag protocol (pcg_common.cuh) and the
+// in-kernel halo gate of the SpMV (spmv_tma.cuh).
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded spin: true when *p reaches `want` (exactly, or at least with `at_least`).  2^24 polls are
+// about 2 s; the first exchange of a solve passes a larger bound (ranks arrive with host-side skew).
+__device__ __forceinline__ bool spin_until(const long long* p, long long want, bool at_least, int polls = 1 << 24) {
+  for (int i = 0; i < polls; ++i) {
+    const long long v = ld_acquire_sys(p);
+    if (at_least ? v >= want : v == want) return true;
+    __nanosleep(100);
+  }
+  return false;
+}
+
 // Streaming (evict-first) loads for data read exactly once per kernel: keeps L2 for the vectors.
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }

@@ -8,17 +8,22 @@
 // happens INSIDE the three solver kernels of an iteration (pcg.cu, primitives in pcg_common.cuh),
 // which stay the only launches of the CUDA graph:
 //
-//   SpMV       last block: publish this rank's p.Ap to every rank's slot array (one warp, NVLink stores)
+//   SpMV       interior tiles first; a consumer group looks at the neighbours' halo tags only right
+//              before its first face tile (HaloGate, spmv_tma.cuh), so the halo exchange hides behind
+//              the interior of the slab.  Last block: publish this rank's p.Ap to every rank's slot
+//              array (one warp, NVLink stores)
 //   update     every CTA: collect the world's p.Ap from the own slot array (local L2 polls), add
 //              in rank order -> alpha; last block: publish (r.z, r.r)
 //   direction  every CTA: collect (r.z, r.r) -> beta / convergence; the boundary rows of the new p
 //              are stored straight into the neighbours' halo rows while p is written; last block:
-//              release the iteration tag to the neighbours and wait for theirs
+//              release the iteration tag to the neighbours (nobody waits at a kernel boundary)
+// (single-reduction recurrence: update + direction are one kernel, one reduction per iteration.)
 //
-// The first version used three extra single-purpose kernels per iteration (halo push, two
-// all-reduces: 6 launches instead of 3); they remain for the one exchange after the init kernel.
 // Every rank forms bitwise identical sums (rank order, no atomics), hence identical convergence
 // decisions.  Spins are bounded: a peer that never arrives raises FEA_ERR_PEER instead of hanging.
+// Halo rows are reused safely without a second handshake: a neighbour overwrites them in its vector
+// kernel of iteration k, which starts only after it has collected every rank's p.Ap of iteration k,
+// i.e. after this rank's SpMV k (the reader of the old rows) has finished.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -28,42 +33,50 @@
 
 namespace fea {
 
-// kind 0: (rz, bnorm2) after init; kind 1: pap after step 1; kind 2: (rz_new, rr) after step 2.
-__global__ void __launch_bounds__(32) p2p_allreduce_kernel(PeerView pv, PcgState* st, int kind) {
-  if (st->done) return;
+// First exchange of a solve (after the init kernel): world sums of (r.z, ||b||^2), and a check that
+// every rank runs the same recurrence (`algo` rides in the slot's spare word).  It is the only point
+// where ranks meet with host-side skew (each rank sliced, copied and assembled its slab on its own),
+// so its spin bound is ~1 min instead of the ~2 s of the per-iteration exchanges.
+__global__ void __launch_bounds__(32) p2p_init_exchange_kernel(PeerView pv, PcgState* st) {
   const int lane = threadIdx.x;
-  // iteration this exchange belongs to: step 2 has already incremented st->iter
-  const long long k = kind == 2 ? st->iter - 1 : st->iter;
-  double mine0, mine1;
-  if (kind == 0) {
-    mine0 = st->rz;
-    mine1 = st->bnorm2;
-  } else if (kind == 1) {
-    mine0 = st->pap;
-    mine1 = 0.0;
-  } else {
-    mine0 = st->rz_new;
-    mine1 = st->rr;
+  constexpr int kind = 0;
+  const long long k = 0, tag = peer_tag(pv, k);
+  if (lane < pv.world) {
+    PeerSlot* dst = &pv.hdr[lane]->slots[0][kind][pv.rank];
+    dst->v[0] = st->rz;
+    dst->v[1] = st->bnorm2;
+    dst->pad = pv.algo;
+    __threadfence_system();
+    st_release_sys(&dst->tag, tag);
   }
-  peer_publish(pv, kind, k, mine0, mine1);
-  double s0, s1;
-  const bool all_ok = peer_collect(pv, kind, k, s0, s1);
+  double v0 = 0.0, v1 = 0.0;
+  bool ok = true;
+  if (lane < pv.world) {
+    const PeerSlot* src = &pv.hdr[pv.rank]->slots[0][kind][lane];
+    ok = spin_until(&src->tag, tag, false, 1 << 27);
+    v0 = ld_volatile_f64(&src->v[0]);
+    v1 = ld_volatile_f64(&src->v[1]);
+    ok = ok && ld_acquire_sys(&src->pad) == pv.algo;
+  }
+  ok = __all_sync(kFull, ok);
+  double s0 = 0.0, s1 = 0.0;
+  for (int r = 0; r < pv.world; ++r) {
+    s0 += __shfl_sync(kFull, v0, r);
+    s1 += __shfl_sync(kFull, v1, r);
+  }
   if (lane == 0) {
-    if (!all_ok) {
+    if (!ok) {
       peer_failure(pv, st);
-    } else if (kind == 0) {
+    } else {
       st->rz = s0;
       st->bnorm2 = s1;
-      st->rr = s1;
-    } else if (kind == 1) {
-      st->pap = s0;
-    } else {
-      st->rz_new = s0;
       st->rr = s1;
     }
   }
 }
 
+// Halo rows of the initial p (later iterations store them from inside the vector kernels); the tag
+// is released by the last block, nobody waits: the first SpMV gates its face tiles on it.
 __global__ void __launch_bounds__(256) p2p_halo_kernel(PeerView pv, PcgState* st) {
   __shared__ bool s_last;
   if (st->done) return;
@@ -84,10 +97,6 @@ __global__ void __launch_bounds__(256) p2p_halo_kernel(PeerView pv, PcgState* st
   __threadfence_system();
   if (pv.lower >= 0) st_release_sys(&pv.hdr[pv.lower]->halo_tag[1], tag);  // I am its upper neighbour
   if (pv.upper >= 0) st_release_sys(&pv.hdr[pv.upper]->halo_tag[0], tag);
-  bool ok = true;
-  if (pv.lower >= 0) ok = spin_until(&own->halo_tag[0], tag, true) && ok;
-  if (pv.upper >= 0) ok = spin_until(&own->halo_tag[1], tag, true) && ok;
-  if (!ok) peer_failure(pv, st);
 }
 
 }  // namespace fea
@@ -127,7 +136,7 @@ extern "C" int fea_comm_ipc_close(void* ptr) { return check(cudaIpcCloseMemHandl
 extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t* node_rowptr_owned,
                                  const int32_t* node_colidx, const double* values, int32_t max_coupled,
                                  const double* dinv, const double* b, double* x, double tol, int32_t max_iter,
-                                 void* work, size_t work_bytes, const fea_peer_comm* comm,
+                                 void* work, size_t work_bytes, double* history, const fea_peer_comm* comm,
                                  fea_pcg_result* result_host, void* stream_) {
   cudaStream_t caller = static_cast<cudaStream_t>(stream_);
   if (!node_rowptr_owned || !node_colidx || !values || !dinv || !b || !x || !work || !comm || !result_host)
@@ -159,6 +168,22 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   pv.lower = comm->lower_peer;
   pv.upper = comm->upper_peer;
   pv.epoch = comm->epoch;
+  // The recurrence must be the same on every rank: chosen from a rank-invariant size (slabs are uneven,
+  // a per-rank choice could straddle the threshold), or given by the caller; verified in the first exchange.
+  const bool multi = comm->world > 1;
+  const int algo = comm->algo == 0 || comm->algo == 1
+                       ? comm->algo
+                       : pcg_algorithm(comm->max_rank_dof > 0 ? comm->max_rank_dof : n, multi);
+  pv.algo = algo;
+  const int64_t n_tiles = ceil_div(n_owned_nodes, kTileNodes);
+  pv.lower_tiles = (int)std::min<int64_t>(n_tiles, ceil_div(std::max<int64_t>(comm->boundary_lower_nodes, 0), kTileNodes));
+  {
+    // tiles that contain any of the last boundary_upper_nodes owned nodes
+    const int64_t first_node = n_owned_nodes - std::min<int64_t>(std::max<int64_t>(comm->boundary_upper_nodes, 0), n_owned_nodes);
+    pv.upper_tiles = comm->boundary_upper_nodes > 0 ? (int)(n_tiles - first_node / kTileNodes) : 0;
+  }
+  if (pv.lower < 0) pv.lower_tiles = 0;
+  if (pv.upper < 0) pv.upper_tiles = 0;
   for (int i = 0; i < comm->world; ++i) {
     if (!comm->comm[i]) return FEA_ERR_INVALID;
     pv.hdr[i] = static_cast<CommHeader*>(comm->comm[i]);
@@ -198,25 +223,36 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   if (rc == FEA_OK) rc = check(cudaStreamWaitEvent(stream, ev_order, 0));
 
   const unsigned vb = vec_blocks(n);
-  const bool multi = comm->world > 1;
   const unsigned halo_blocks = 8;
-  auto exchange = [&](int kind) {
-    if (multi) p2p_allreduce_kernel<<<1, 32, 0, stream>>>(pv, state, kind);
+  auto exchange = [&]() {
+    if (multi) p2p_init_exchange_kernel<<<1, 32, 0, stream>>>(pv, state);
   };
   auto halo = [&]() {
     if (multi) p2p_halo_kernel<<<halo_blocks, 256, 0, stream>>>(pv, state);
   };
   const PeerView* pv_it = multi ? pv_dev : nullptr;
-  const int algo = pcg_algorithm(n, multi);
-  auto iteration = [&]() -> int {
+  // measurement hook (as in fea_pcg_solve): CUDA-event pairs around one SpMV launch per chunk
+  constexpr int kMaxSamples = 256;
+  cudaEvent_t* sample_ev = nullptr;
+  int n_samples = 0;
+  int sample_iter[kMaxSamples];
+  if (profile().enabled) {
+    sample_ev = new cudaEvent_t[2 * kMaxSamples];
+    for (int i = 0; i < 2 * kMaxSamples; ++i) cudaEventCreate(&sample_ev[i]);
+  }
+  int64_t enqueued = 0;
+  auto iteration = [&](bool sample) -> int {
+    if (sample) sample_iter[n_samples] = (int)enqueued;
+    if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
     const int r1 = pcg_step_spmv(d, n_owned_nodes, node_rowptr_owned, node_colidx, values, p_ext, ap,
                                  comm->own_offset_nodes, state, partials, stream, &plan, pv_it);
+    if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
     if (algo == 1) {  // p_own holds u = dinv r here (the SpMV input)
-      pcg_cgcg_kernel<<<cgcg_blocks(n), 256, 0, stream>>>(n, dinv, p_own, ap, p2, s_vec, x, r, state, partials, nullptr,
+      pcg_cgcg_kernel<<<cgcg_blocks(n), 256, 0, stream>>>(n, dinv, p_own, ap, p2, s_vec, x, r, state, partials, history,
                                                           pv_it);
     } else {
       pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials, pv_it);
-      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, nullptr, pv_it);
+      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, history, pv_it);
     }
     return r1;
   };
@@ -231,22 +267,21 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     rc = check(cudaMemcpyAsync(const_cast<PeerView*>(pv_dev), &pv, sizeof(PeerView), cudaMemcpyHostToDevice, stream));
   if (rc == FEA_OK) {
     pcg_init_kernel<<<vb, 256, 0, stream>>>(n, b, dinv, x, r, p_own, tol, max_iter, state, partials);
-    exchange(0);
+    exchange();
     halo();
     rc = check_launch(multi ? 3 : 1);
   }
   const int chunk = 32;
-  int64_t enqueued = 0;
   int slot = 0;
   bool pending[2] = {false, false};
   bool finished = false;
   if (rc == FEA_OK && max_iter >= chunk && std::getenv("FEA_PCG_NO_GRAPH") == nullptr) {
-    rc = iteration();  // warm-up outside capture
+    rc = iteration(false);  // warm-up outside capture
     if (rc == FEA_OK) rc = check_launch(launches_per_iteration);
     enqueued += 1;
     cudaGraph_t graph = nullptr;
     if (rc == FEA_OK && cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      for (int it = 0; it < chunk; ++it) iteration();
+      for (int it = 0; it < chunk - 1; ++it) iteration(false);
       if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || graph == nullptr ||
           cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess)
         graph_exec = nullptr;
@@ -256,10 +291,12 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   }
   while (rc == FEA_OK && !finished) {
     const int todo = (int)std::min<int64_t>(chunk, enqueue_limit - enqueued);
-    if (graph_exec != nullptr && todo == chunk) {
-      rc = check(cudaGraphLaunch(graph_exec, stream));
+    if (graph_exec != nullptr && todo == chunk) {  // one plain iteration (carries the timing sample) + the graph
+      rc = iteration(sample_ev != nullptr && n_samples < kMaxSamples);
+      if (rc == FEA_OK) rc = check(cudaGraphLaunch(graph_exec, stream));
     } else {
-      for (int it = 0; it < todo && rc == FEA_OK; ++it) rc = iteration();
+      for (int it = 0; it < todo && rc == FEA_OK; ++it)
+        rc = iteration(sample_ev != nullptr && it == 0 && n_samples < kMaxSamples);
     }
     if (rc == FEA_OK) rc = check_launch(launches_per_iteration * todo);
     if (rc != FEA_OK) break;
@@ -291,8 +328,20 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     const double rr = s.done ? s.rr_final : s.rr;
     result_host->rel_residual = s.bnorm2 > 0.0 ? std::sqrt(rr / s.bnorm2) : 0.0;
     profile().pcg_iterations += s.iter;
+    for (int i = 0; i < n_samples; ++i) {
+      if (sample_iter[i] >= s.iter) break;  // launches after convergence are no-ops
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sample_ev[2 * i], sample_ev[2 * i + 1]) == cudaSuccess) {
+        profile().spmv_ms += ms;
+        profile().spmv_samples += 1;
+      }
+    }
   } else if (stream != nullptr) {
     cudaStreamSynchronize(stream);
+  }
+  if (sample_ev != nullptr) {
+    for (int i = 0; i < 2 * kMaxSamples; ++i) cudaEventDestroy(sample_ev[i]);
+    delete[] sample_ev;
   }
   if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
   if (stream != nullptr) {

@@ -21,13 +21,38 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "pcg_common.cuh"
 
 namespace fea {
 
+// Per-device facts and launch configurations.  cudaFuncSetAttribute and the occupancy numbers are
+// per device: a process that drives several GPUs (the C ABI allows it) must not reuse device 0's.
+constexpr int kMaxDevices = 64;
+struct DeviceInfo {
+  int sm_count = 0, smem_optin = 0;
+};
+static const DeviceInfo* device_info() {
+  static DeviceInfo info[kMaxDevices];
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  DeviceInfo& di = info[dev];
+  if (di.sm_count == 0) {
+    cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&di.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  return &di;
+}
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+
 TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_colidx, int64_t n_nodes) {
-  static int sm_count = 0, smem_optin = 0;
   TmaPlan plan;
   plan.ok = false;
   plan.max_grid = 0;
@@ -35,27 +60,19 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
   plan.layout = TmaLayout{0, 0, 0, 0};
   if (max_coupled < 1 || d < 1 || d > 3) return plan;
   if ((reinterpret_cast<uintptr_t>(values) & 15u) || (reinterpret_cast<uintptr_t>(node_colidx) & 15u)) return plan;
-  if (sm_count == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return plan;
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  }
-  if (sm_count <= 0 || smem_optin <= 0) return plan;
+  const DeviceInfo* di = device_info();
+  if (di == nullptr || di->sm_count <= 0 || di->smem_optin <= 0) return plan;
   if (n_nodes >= (int64_t)INT32_MAX / 4) return plan;
   // Shape of the pipeline: consumer groups per CTA, ring stages per CTA, CTAs (rings) per SM.
-  static int cfg_groups = 0, cfg_stages = 0, cfg_ctas = 0;
-  if (cfg_groups == 0) {
-    cfg_groups = 2, cfg_stages = 2, cfg_ctas = 3;  // best of the sweep on B200: profiles/tma_sweep_r01.log
-    if (const char* env = std::getenv("FEA_TMA_CFG")) {
-      int g = 0, s = 0, c = 0;
-      if (std::sscanf(env, "%d,%d,%d", &g, &s, &c) == 3 && g >= 1 && g <= kTmaMaxGroups && s >= 1 &&
-          s <= kTmaMaxStages && c >= 1 && c <= 8)
-        cfg_groups = g, cfg_stages = s, cfg_ctas = c;
-    }
+  int cfg_groups = 2, cfg_stages = 2, cfg_ctas = 3;  // best of the sweep on B200: profiles/tma_sweep_r01.log
+  if (const char* env = std::getenv("FEA_TMA_CFG")) {
+    int g = 0, s = 0, c = 0;
+    if (std::sscanf(env, "%d,%d,%d", &g, &s, &c) == 3 && g >= 1 && g <= kTmaMaxGroups && s >= 1 &&
+        s <= kTmaMaxStages && c >= 1 && c <= 8)
+      cfg_groups = g, cfg_stages = s, cfg_ctas = c;
   }
   // shared memory per SM is split between the CTAs; keep ~1 KB per CTA for static smem + reserve
-  const size_t per_cta = ((size_t)smem_optin + 1024) / cfg_ctas - 2048;
+  const size_t per_cta = ((size_t)di->smem_optin + 1024) / cfg_ctas - 2048;
   // The ring length is a multiple of the group count (a stage is always consumed by the same
   // group); drop groups until one ring fits.
   int groups = cfg_groups;
@@ -66,7 +83,7 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
   }
   if (plan.layout.stages < 1) return plan;  // tile wider than shared memory
   const int64_t tiles = ceil_div(n_nodes, kTileNodes);
-  plan.max_grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * cfg_ctas));
+  plan.max_grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)di->sm_count * cfg_ctas));
   plan.groups = groups;
   plan.ok = true;
   return plan;
@@ -103,8 +120,19 @@ __device__ __forceinline__ void finish_pap(const double* partials, double* s_red
   }
   if (pv != nullptr) {
     __syncthreads();
+    if (threadIdx.x == 0 && pv->hdr[pv->rank]->error != 0) peer_failure(*pv, st);  // a halo gate timed out
     if (threadIdx.x < 32) peer_publish(*pv, 1, st->iter, s_red[0], 0.0);
   }
+}
+
+// Multi-GPU: hold the calling thread until the neighbours' halo rows of this iteration have landed.
+__device__ __forceinline__ bool wait_halo(const PeerView& pv, long long iter) {
+  const long long tag = peer_tag(pv, iter);
+  CommHeader* own = pv.hdr[pv.rank];
+  bool ok = true;
+  if (pv.lower >= 0) ok = spin_until(&own->halo_tag[0], tag, true) && ok;
+  if (pv.upper >= 0) ok = spin_until(&own->halo_tag[1], tag, true) && ok;
+  return ok;
 }
 
 template <int D>
@@ -136,6 +164,10 @@ pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const 
                 int64_t p_row_offset, PcgState* st, double* partials, const PeerView* pv) {
   __shared__ double s_red[32];
   if (st->done) return;
+  if (pv != nullptr) {  // no tile ordering here: every block waits for the halo before its first gather
+    if (threadIdx.x == 0 && !wait_halo(*pv, st->iter)) pv->hdr[pv->rank]->error = 1;
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* p_own = p + p_row_offset * D;
   double dot = 0.0;
@@ -158,7 +190,7 @@ pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const 
 }
 
 // step 1, bulk-copy pipeline variant (spmv_tma.cuh)
-template <int D, int G>
+template <int D, int G, bool GATED>
 __global__ void __launch_bounds__(tma_threads(D, G))
 pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                     const double* __restrict__ values, const double* __restrict__ p, double* __restrict__ ap,
@@ -168,10 +200,52 @@ pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const 
   __shared__ double s_red[32];
   if (st->done) return;
   double dot = 0.0;
-  spmv_tma_body<D, G, true>(n_nodes, node_rowptr, node_colidx, values, p, ap, p_own, stages, val_cap, col_cap, s_tma,
-                            dot);
+  HaloGate gate;
+  if (GATED) {  // multi-GPU: interior tiles first, the halo tags are only looked at before a face tile
+    CommHeader* own = pv->hdr[pv->rank];
+    gate.tag_lower = pv->lower >= 0 ? &own->halo_tag[0] : nullptr;
+    gate.tag_upper = pv->upper >= 0 ? &own->halo_tag[1] : nullptr;
+    gate.want = peer_tag(*pv, st->iter);
+    gate.lower_tiles = pv->lower_tiles;
+    gate.upper_tiles = pv->upper_tiles;
+    gate.error = &own->error;
+  }
+  spmv_tma_body<D, G, true, GATED>(n_nodes, node_rowptr, node_colidx, values, p, ap, p_own, stages, val_cap, col_cap,
+                                   s_tma, dot, GATED ? &gate : nullptr);
   const double total = block_sum(dot, s_red);
   if (publish_partials(partials, 1, &total, &st->counter[0])) finish_pap(partials, s_red, st, pv);
+}
+
+// Launch configuration of one kernel instance, cached per device.
+struct GridCache {
+  int grid[kMaxDevices] = {};
+  long long key[kMaxDevices];
+  std::mutex mu;
+  GridCache() {
+    for (auto& k : key) k = -1;
+  }
+};
+
+template <typename Kernel>
+static int tma_grid(GridCache& cache, Kernel kernel, const TmaPlan& plan, int threads, int* grid_out) {
+  const TmaLayout& L = plan.layout;
+  const long long key = ((long long)plan.max_grid << 32) | (long long)L.smem_bytes;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(cache.mu);
+  if (cache.key[dev] != key) {
+    FEA_TRY(check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_bytes)));
+    // Persistent kernel: never launch more CTAs than can be resident at once (a partial second
+    // wave would idle most of the chip), whatever registers / shared memory allow for this variant.
+    int per_sm = 0, sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, L.smem_bytes) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 1;
+    cache.grid[dev] = std::min(plan.max_grid, per_sm * sms);
+    cache.key[dev] = key;
+  }
+  *grid_out = cache.grid[dev];
+  return FEA_OK;
 }
 
 template <int D, int G>
@@ -179,41 +253,23 @@ static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int3
                       const double* values, const double* x, double* y, int64_t off, PcgState* st, double* partials,
                       cudaStream_t stream, const PeerView* pv) {
   const TmaLayout& L = plan.layout;
-  // Persistent kernel: never launch more CTAs than can be resident at once (a partial second
-  // wave would idle most of the chip), whatever registers / shared memory allow for this variant.
-  auto resident_grid = [&](auto kernel) -> int {
-    int per_sm = 0, sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, tma_threads(D, G), L.smem_bytes) !=
-            cudaSuccess || per_sm < 1)
-      per_sm = 1;
-    return std::min(plan.max_grid, per_sm * sms);
-  };
-  const long long key = ((long long)plan.max_grid << 32) | (long long)L.smem_bytes;
   const int n = (int)n_nodes;
-  if (dot) {
-    static int grid_cache = 0;
-    static long long grid_key = -1;
-    if (grid_key != key) {
-      FEA_TRY(check(cudaFuncSetAttribute(pcg_spmv_tma_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)L.smem_bytes)));
-      grid_cache = resident_grid(pcg_spmv_tma_kernel<D, G>);
-      grid_key = key;
-    }
-    pcg_spmv_tma_kernel<D, G><<<grid_cache, tma_threads(D, G), L.smem_bytes, stream>>>(
+  int grid = 0;
+  if (dot && pv != nullptr) {
+    static GridCache cache;
+    FEA_TRY(tma_grid(cache, pcg_spmv_tma_kernel<D, G, true>, plan, tma_threads(D, G), &grid));
+    pcg_spmv_tma_kernel<D, G, true><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(
         n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, pv);
+  } else if (dot) {
+    static GridCache cache;
+    FEA_TRY(tma_grid(cache, pcg_spmv_tma_kernel<D, G, false>, plan, tma_threads(D, G), &grid));
+    pcg_spmv_tma_kernel<D, G, false><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(
+        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, nullptr);
   } else {
-    static int grid_cache = 0;
-    static long long grid_key = -1;
-    if (grid_key != key) {
-      FEA_TRY(check(cudaFuncSetAttribute(spmv_tma_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)L.smem_bytes)));
-      grid_cache = resident_grid(spmv_tma_kernel<D, G>);
-      grid_key = key;
-    }
-    spmv_tma_kernel<D, G><<<grid_cache, tma_threads(D, G), L.smem_bytes, stream>>>(n, rp, ci, values, x, y, L.stages,
-                                                                              L.val_cap, L.col_cap);
+    static GridCache cache;
+    FEA_TRY(tma_grid(cache, spmv_tma_kernel<D, G>, plan, tma_threads(D, G), &grid));
+    spmv_tma_kernel<D, G><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(n, rp, ci, values, x, y, L.stages,
+                                                                        L.val_cap, L.col_cap);
   }
   return FEA_OK;
 }
@@ -240,6 +296,31 @@ static int dispatch_tma(int d, const TmaPlan& plan, bool dot, int64_t n_nodes, c
     case 3: return launch_tma_g<3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
     default: return FEA_ERR_INVALID;
   }
+}
+
+// Stagnation guard (one thread, once per iteration, identical on every rank: rr is the world's sum).
+// A singular reduced system with an inconsistent right-hand side -- an under-constrained body -- never
+// breaks down in exact terms (p.Ap stays > 0) and would iterate to max_iter = 10 n; its residual stops
+// improving instead.  If the best ||r||^2 seen has not dropped by 1 % within `window` iterations the
+// solve ends with FEA_ERR_STAGNATION.  window = max(10000, max_iter / 1000): far longer than any plateau
+// of a convergent run (config 4 needs 8.5 k iterations in total), 1000x shorter than max_iter.
+__device__ __forceinline__ bool stall_improved(const PcgState* st, double rr) {
+  return !(rr >= 0.99 * st->spare[1]) || st->spare[1] == 0.0;
+}
+__device__ __forceinline__ bool stall_check(const PcgState* st, double rr, int iter) {  // read-only
+  if (stall_improved(st, rr)) return false;
+  return iter - (int)st->spare[2] >= max(10000, st->max_iter / 1000);
+}
+__device__ __forceinline__ void stall_note(PcgState* st, double rr, int iter) {  // one thread per iteration
+  if (stall_improved(st, rr)) {
+    st->spare[1] = rr;
+    st->spare[2] = (double)iter;
+  }
+}
+__device__ __forceinline__ bool stagnated(PcgState* st, double rr, int iter) {
+  const bool stalled = stall_check(st, rr, iter);
+  stall_note(st, rr, iter);
+  return stalled;
 }
 
 // step 2
@@ -420,26 +501,23 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
       finished = true;
     } else {
       st->rz = rz_new;
-      if (iter >= st->max_iter) {
+      const bool stalled = stagnated(st, rr, iter);
+      if (iter >= st->max_iter || stalled) {
         st->done = 1;
-        st->status = FEA_ERR_MAXITER;
+        st->status = stalled ? FEA_ERR_STAGNATION : FEA_ERR_MAXITER;
         st->rr_final = rr;
+        finished = true;
       }
     }
     st->counter[2] = 0;
     if (pv != nullptr && !finished) {
       // every block's halo stores are fenced (above) and counted: release the iteration tag to the
-      // neighbours, then hold the kernel until their rows of p have landed here, so that the next
-      // SpMV (a plain kernel boundary later) gathers a complete halo.
+      // neighbours.  Nobody waits here: the next SpMV looks at the neighbours' tags right before its
+      // first face tile (HaloGate, spmv_tma.cuh), after the interior of the slab.
       const long long tag = peer_tag(*pv, iter);
       __threadfence_system();
       if (pv->lower >= 0) st_release_sys(&pv->hdr[pv->lower]->halo_tag[1], tag);  // I am its upper neighbour
       if (pv->upper >= 0) st_release_sys(&pv->hdr[pv->upper]->halo_tag[0], tag);
-      CommHeader* own = pv->hdr[pv->rank];
-      bool ok = true;
-      if (pv->lower >= 0) ok = spin_until(&own->halo_tag[0], tag, true) && ok;
-      if (pv->upper >= 0) ok = spin_until(&own->halo_tag[1], tag, true) && ok;
-      if (!ok) peer_failure(*pv, st);
     }
   }
 }
@@ -493,7 +571,8 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
   }
   const double bnorm2 = st->bnorm2;
   const bool converged = rr <= st->tol2 * bnorm2;  // also covers a zero right-hand side
-  const bool exhausted = !converged && iter >= st->max_iter;
+  const bool stalled = !converged && iter > 0 && stall_check(st, rr, iter);
+  const bool exhausted = !converged && (iter >= st->max_iter || stalled);
   double beta = 0.0, alpha = 0.0;
   bool breakdown = false;
   if (!converged && !exhausted) {
@@ -511,7 +590,8 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       if (history != nullptr && iter >= 1 && iter <= st->max_iter) history[iter - 1] = sqrt(rr / bnorm2);
       st->done = 1;
-      st->status = converged ? FEA_OK : (breakdown ? FEA_ERR_BREAKDOWN : FEA_ERR_MAXITER);
+      st->status = converged ? FEA_OK
+                             : (breakdown ? FEA_ERR_BREAKDOWN : (stalled ? FEA_ERR_STAGNATION : FEA_ERR_MAXITER));
       st->rr = rr;
       st->rr_final = rr;
     }
@@ -568,6 +648,7 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
     const double b = reduce_partials(partials + kMaxPartials, s_red);
     if (threadIdx.x == 0) {
       if (history != nullptr && iter >= 1 && iter <= st->max_iter) history[iter - 1] = sqrt(rr / bnorm2);
+      if (iter > 0) stall_note(st, rr, iter);
       st->rz = gamma;    // gamma_old of the next iteration
       st->rz_new = a;    // with peers: this rank's partial sums (the next step 2 collects the world's)
       st->rr = b;
@@ -585,11 +666,7 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
         __threadfence_system();
         if (pv->lower >= 0) st_release_sys(&pv->hdr[pv->lower]->halo_tag[1], tag);
         if (pv->upper >= 0) st_release_sys(&pv->hdr[pv->upper]->halo_tag[0], tag);
-        CommHeader* own = pv->hdr[pv->rank];
-        bool ok = true;
-        if (pv->lower >= 0) ok = spin_until(&own->halo_tag[0], tag, true) && ok;
-        if (pv->upper >= 0) ok = spin_until(&own->halo_tag[1], tag, true) && ok;
-        if (!ok) peer_failure(*pv, st);
+        // no wait here: the next SpMV gates its face tiles on the neighbours' tags (HaloGate)
       }
     }
   }
@@ -738,9 +815,12 @@ extern "C" size_t fea_pcg_workspace(int64_t n_dof) {
 // otherwise ~35 us), so the vector kernels ask for the SpMV's carve-out: they stream and do not
 // need L1.
 void fea::pcg_match_carveout() {
-  static bool done = false;
-  if (done) return;
-  done = true;
+  static bool done[kMaxDevices] = {};
+  static std::mutex mu;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  if (done[dev]) return;
+  done[dev] = true;
   cudaFuncSetAttribute(pcg_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(pcg_direction_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                        cudaSharedmemCarveoutMaxShared);

@@ -63,31 +63,11 @@ struct PeerView {
   long long lower_cnt, upper_cnt;  // doubles
   long long lower_off, upper_off;  // offsets of the mirrored ranges inside p_own (doubles)
   long long epoch;
+  int lower_tiles, upper_tiles;    // SpMV tiles next to the lower / upper slab face (HaloGate, spmv_tma.cuh)
+  int algo, pad;
 };
 static_assert(sizeof(PeerView) <= kCommHeaderBytes - kCommViewOffset, "PeerView fits the header page");
 
-__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
-  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
-  long long v;
-  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ld_volatile_f64(const double* p) {
-  double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-// Bounded spin (about 2 s): true when *p reaches `want` (exactly, or at least with `at_least`).
-__device__ __forceinline__ bool spin_until(const long long* p, long long want, bool at_least) {
-  for (int i = 0; i < (1 << 24); ++i) {
-    const long long v = ld_acquire_sys(p);
-    if (at_least ? v >= want : v == want) return true;
-    __nanosleep(100);
-  }
-  return false;
-}
 __device__ __forceinline__ long long peer_tag(const PeerView& pv, long long k) { return (pv.epoch << 32) | (k + 1); }
 // A peer never delivered: stop the solve with FEA_ERR_PEER instead of hanging the GPU.
 __device__ __forceinline__ void peer_failure(const PeerView& pv, PcgState* st) {

@@ -123,24 +123,43 @@ inline TmaLayout tma_layout(int d, int groups, int maxc, int max_stages, size_t 
 // Byte ranges of one tile, rounded out to 16 B; `direct` when the rounding would run past the end
 // of the arrays (only the last tile(s) of the matrix): those are read with plain loads instead.
 struct TileRange {
-  int v_lo, v_hi, c_lo, c_hi;  // element indices (< 2^31: the library requires int32 nnz)
+  // element indices: value offsets are 64-bit (d*d*nnz_blocks passes 2^31 at ~26 M DOF on a hex8 mesh,
+  // 17 GB of values -- small for a 180 GB part); block offsets fit int32 (node_rowptr is int32)
+  int64_t v_lo, v_hi;
+  int c_lo, c_hi;
   bool direct;
 };
 template <int D>
 __device__ __forceinline__ TileRange tile_range(int r0, int r1, int total_cols) {
   TileRange t;
-  t.v_lo = (D * D * r0) & ~1;
-  t.v_hi = (D * D * r1 + 1) & ~1;
+  t.v_lo = ((int64_t)(D * D) * r0) & ~(int64_t)1;
+  t.v_hi = ((int64_t)(D * D) * r1 + 1) & ~(int64_t)1;
   t.c_lo = r0 & ~3;
-  t.c_hi = (r1 + 3) & ~3;
-  t.direct = t.v_hi > D * D * total_cols || t.c_hi > total_cols;
+  t.c_hi = (int)(((int64_t)r1 + 3) & ~(int64_t)3);
+  t.direct = t.v_hi > (int64_t)(D * D) * total_cols || t.c_hi > total_cols || t.c_hi < 0;
   return t;
 }
+
+// Multi-GPU halo gate (fea_pcg_solve_p2p).  The rows of x that the z-neighbours own are stored into
+// this rank's x by the neighbours' vector kernels over NVLink, followed by a tag.  Only the tiles
+// next to a slab face gather such rows, so the sweep starts `lower_tiles` tiles in (interior first;
+// the lower-face tiles wrap around to the very end) and a consumer group only looks at the tag right
+// before its first boundary tile: the halo exchange hides behind the interior of the SpMV.  Boundary
+// tiles gather x with L2-coherent loads (ld.global.cg): a 128-byte line that straddles the owned/halo
+// border may sit in L1 from an interior tile, with the halo part not yet delivered.
+struct HaloGate {
+  const long long* tag_lower;  // this rank's halo_tag[0] / [1]; nullptr without that neighbour
+  const long long* tag_upper;
+  long long want;              // tag value of the iteration being multiplied
+  int lower_tiles;             // tiles [0, lower_tiles) gather lower-halo rows
+  int upper_tiles;             // tiles [n_tiles - upper_tiles, n_tiles) gather upper-halo rows
+  int* error;                  // set to 1 when a neighbour never delivers
+};
 
 // Component b of one DOF row against x: sum_k vrow[D*k + b] * x[D*cols[k] + b].
 // `vrow` / `cols` may point to shared or global memory.  Every gather of a round is issued
 // before the first FMA.
-template <int D>
+template <int D, bool COHERENT = false>
 __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t* cols, int cnt, int b,
                                                const double* __restrict__ x) {
   double acc = 0.0;
@@ -151,7 +170,10 @@ __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t
 #pragma unroll
     for (int u = 0; u < kTmaUnroll; ++u) {
       const int k = k0 + u;
-      xv[u] = k < cnt ? __ldg(xb + (int64_t)D * cols[k]) : 0.0;
+      if (COHERENT)
+        xv[u] = k < cnt ? __ldcg(xb + (int64_t)D * cols[k]) : 0.0;
+      else
+        xv[u] = k < cnt ? __ldg(xb + (int64_t)D * cols[k]) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < kTmaUnroll; ++u) {
@@ -163,12 +185,13 @@ __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t
 }
 
 // DOT: also accumulate sum_owned x_own[row] * y[row] (the PCG p.Ap); the caller reduces `dot`.
-template <int D, int G, bool DOT>
+template <int D, int G, bool DOT, bool GATED = false>
 __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __restrict__ node_rowptr,
                                               const int32_t* __restrict__ node_colidx,
                                               const double* __restrict__ values, const double* __restrict__ x,
                                               double* __restrict__ y, const double* __restrict__ x_own, int stages,
-                                              int val_cap, int col_cap, unsigned char* smem, double& dot) {
+                                              int val_cap, int col_cap, unsigned char* smem, double& dot,
+                                              const HaloGate* gate = nullptr) {
   constexpr int DD = D * D;
   constexpr int ROWS = D * kTileNodes;  // rows per tile
   constexpr int ITEMS = tma_items(D);   // (row, b) pairs per tile
@@ -192,6 +215,12 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
   const int n_tiles = (n_nodes + kTileNodes - 1) / kTileNodes;
   const int total_cols = node_rowptr[n_nodes];
   const int stride = (int)gridDim.x;
+  // sweep position t -> tile: rotated by the lower-face tiles when gated (interior first)
+  const int rot = GATED ? gate->lower_tiles : 0;
+  auto tile_of = [&](int64_t t) -> int {
+    const int64_t p = t + rot;
+    return (int)(p < n_tiles ? p : p - n_tiles);
+  };
 
   if (warp == G * GW) {
     // ------------------------------------------------------------------ producer
@@ -201,7 +230,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
       const int64_t t = blockIdx.x + (int64_t)stride * q;
       a0 = a1 = 0;
       if (t < n_tiles) {
-        const int n0 = (int)t * kTileNodes;
+        const int n0 = tile_of(t) * kTileNodes;
         a0 = node_rowptr[n0];
         a1 = node_rowptr[n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes];
       }
@@ -243,7 +272,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
     // row pointers of this lane's node for the first tile; later tiles are prefetched one ahead
     int r0 = 0, r1 = 0, lo = 0, hi = 0;
     if (tile64 < n_tiles) {
-      const int n0 = (int)tile64 * kTileNodes;
+      const int n0 = tile_of(tile64) * kTileNodes;
       const int n1 = n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes;
       r0 = node_rowptr[n0];
       r1 = node_rowptr[n1];
@@ -253,15 +282,35 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
       }
     }
     int buf_sel = 0;
+    bool seen_lower = false, seen_upper = false;
     for (int q = group; tile64 < n_tiles; q += G) {
-      const int n0 = (int)tile64 * kTileNodes;
+      const int tile = tile_of(tile64);
+      const int n0 = tile * kTileNodes;
       const int n1 = n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes;
       const int node = n0 + node_in_tile;
       const bool active = has_item && node < n1;
+      bool coherent = false;
+      if (GATED) {  // group-uniform: every thread of the group works on the same tile
+        const bool need_lower = tile < gate->lower_tiles, need_upper = tile >= n_tiles - gate->upper_tiles;
+        const bool wait_lower = need_lower && !seen_lower && gate->tag_lower != nullptr;
+        const bool wait_upper = need_upper && !seen_upper && gate->tag_upper != nullptr;
+        if (wait_lower || wait_upper) {
+          if (warp == group * GW && lane == 0) {
+            bool ok = true;
+            if (wait_lower) ok = spin_until(gate->tag_lower, gate->want, true) && ok;
+            if (wait_upper) ok = spin_until(gate->tag_upper, gate->want, true) && ok;
+            if (!ok) *gate->error = 1;
+          }
+          group_barrier(1 + group, GW * 32);
+          seen_lower = seen_lower || wait_lower;
+          seen_upper = seen_upper || wait_upper;
+        }
+        coherent = need_lower || need_upper;
+      }
       tile64 += (int64_t)stride * G;
       int nr0 = 0, nr1 = 0, nlo = 0, nhi = 0;
       if (tile64 < n_tiles) {
-        const int m0 = (int)tile64 * kTileNodes;
+        const int m0 = tile_of(tile64) * kTileNodes;
         const int m1 = m0 + kTileNodes < n_nodes ? m0 + kTileNodes : n_nodes;
         nr0 = node_rowptr[m0];
         nr1 = node_rowptr[m1];
@@ -274,17 +323,21 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
       const int cnt = hi - lo;
       double part = 0.0;
       if (t.direct) {
-        if (active)
-          part = row_part_dot<D>(values + (int64_t)DD * lo + a * D * cnt, node_colidx + lo, cnt, b, x);
+        if (active) {
+          const double* vg = values + (int64_t)DD * lo + a * D * cnt;
+          part = GATED && coherent ? row_part_dot<D, true>(vg, node_colidx + lo, cnt, b, x)
+                                   : row_part_dot<D>(vg, node_colidx + lo, cnt, b, x);
+        }
       } else {
         const int s = q % stages;
         const uint32_t ph = (uint32_t)(q / stages) & 1u;
         mbar_wait(&full[s], ph);
         if (active) {
           const unsigned char* buf = stage0 + (size_t)s * stage_bytes;
-          const double* vs = reinterpret_cast<const double*>(buf) + (DD * lo - t.v_lo);
+          const double* vs = reinterpret_cast<const double*>(buf) + (int)((int64_t)DD * lo - t.v_lo);
           const int32_t* cs = reinterpret_cast<const int32_t*>(buf + sizeof(double) * val_cap) + (lo - t.c_lo);
-          part = row_part_dot<D>(vs + a * D * cnt, cs, cnt, b, x);
+          part = GATED && coherent ? row_part_dot<D, true>(vs + a * D * cnt, cs, cnt, b, x)
+                                   : row_part_dot<D>(vs + a * D * cnt, cs, cnt, b, x);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);

@@ -75,21 +75,49 @@ def node_cuts(n_nodes: int, world: int, layer: int | None = None) -> np.ndarray:
     return cuts.astype(np.int64)
 
 
-def _halo_extent(elements: np.ndarray, lo: int, hi: int):
-    """Elements touching [lo, hi) and the node range they span."""
-    touch = ((elements >= lo) & (elements < hi)).any(axis=1)
-    ids = np.nonzero(touch)[0]
-    if ids.size == 0:
-        return ids, lo, hi
-    sub = elements[ids]
-    return ids, min(int(sub.min()), lo), max(int(sub.max()) + 1, hi)
+def _scan_ranges(elements: np.ndarray, ranges):
+    """For every node range [lo, hi): (element count, first id, last id, min node, max node) of the
+    elements with at least one node inside.  One multi-threaded pass through fea_slab_scan for
+    contiguous int64 / int32 connectivity; numpy otherwise."""
+    elements = np.asarray(elements)
+    if elements.flags.c_contiguous and elements.dtype in (np.int64, np.int32) and elements.ndim == 2:
+        lib = _lib.load()
+        rg = np.ascontiguousarray(np.asarray(ranges, dtype=np.int64).reshape(-1))
+        out = np.empty(5 * len(ranges), dtype=np.int64)
+        _lib.check(lib.fea_slab_scan(elements.ctypes.data, elements.dtype.itemsize, elements.shape[0],
+                                     elements.shape[1], rg.ctypes.data, len(ranges), out.ctypes.data), "fea_slab_scan")
+        return [tuple(int(v) for v in out[5 * i:5 * i + 5]) for i in range(len(ranges))]
+    res = []
+    for lo, hi in ranges:
+        ids = np.nonzero(((elements >= lo) & (elements < hi)).any(axis=1))[0]
+        if ids.size == 0:
+            res.append((0, -1, -1, 0, 0))
+        else:
+            sub = elements[ids]
+            res.append((int(ids.size), int(ids[0]), int(ids[-1]), int(sub.min()), int(sub.max())))
+    return res
 
 
 def plan_slab(elements: np.ndarray, cuts: np.ndarray, rank: int) -> SlabPlan:
     """Everything rank `rank` needs to know, computed locally and identically on every rank."""
+    elements = np.asarray(elements)
     world = len(cuts) - 1
     own_lo, own_hi = int(cuts[rank]), int(cuts[rank + 1])
-    ids, g_lo, g_hi = _halo_extent(elements, own_lo, own_hi)
+    ranges = [(own_lo, own_hi)]
+    if rank > 0:
+        ranges.append((int(cuts[rank - 1]), own_lo))
+    if rank < world - 1:
+        ranges.append((own_hi, int(cuts[rank + 2])))
+    stats = _scan_ranges(elements, ranges)
+    count, first, last, mn, mx = stats[0]
+    if count == 0:
+        ids, g_lo, g_hi = np.empty(0, dtype=np.int64), own_lo, own_hi
+    else:
+        g_lo, g_hi = min(mn, own_lo), max(mx + 1, own_hi)
+        if last - first + 1 == count:  # layer-major meshes: a contiguous element range
+            ids = np.arange(first, last + 1, dtype=np.int64)
+        else:
+            ids = np.nonzero(((elements >= own_lo) & (elements < own_hi)).any(axis=1))[0]
     recv_down = recv_up = send_down = send_up = None
     if g_lo < own_lo:
         if rank == 0 or g_lo < cuts[rank - 1]:
@@ -100,14 +128,16 @@ def plan_slab(elements: np.ndarray, cuts: np.ndarray, rank: int) -> SlabPlan:
             raise ValueError("slab thinner than the mesh bandwidth: halo spans more than one neighbour")
         recv_up = (rank + 1, own_hi, g_hi)
     # what the neighbours need from me = their halo ranges
+    k = 1
     if rank > 0:
-        _, _, nb_hi = _halo_extent(elements, int(cuts[rank - 1]), own_lo)
-        if nb_hi > own_lo:
-            send_down = (rank - 1, own_lo, nb_hi)
+        c, _, _, _, nb_max = stats[k]
+        k += 1
+        if c and nb_max + 1 > own_lo:
+            send_down = (rank - 1, own_lo, nb_max + 1)
     if rank < world - 1:
-        _, nb_lo, _ = _halo_extent(elements, own_hi, int(cuts[rank + 2]))
-        if nb_lo < own_hi:
-            send_up = (rank + 1, nb_lo, own_hi)
+        c, _, _, nb_min, _ = stats[k]
+        if c and nb_min < own_hi:
+            send_up = (rank + 1, nb_min, own_hi)
     return SlabPlan(rank, world, own_lo, own_hi, g_lo, g_hi, ids, send_down, send_up, recv_down, recv_up)
 
 
@@ -153,6 +183,7 @@ class DistInfo:
     rel_residual: float
     status: int
     bnorm: float
+    history: np.ndarray | None = None
 
 
 def distributed_pcg(ops, plan: SlabPlan, d: int, b_owned: torch.Tensor, dinv_owned: torch.Tensor, tol: float = 1e-12,
@@ -301,17 +332,28 @@ class GpuOps:
 class P2PComm:
     """This rank's communication block (header + halo-extended p vector) and the IPC mappings of
     every peer's block, for fea_pcg_solve_p2p.  Cached per slab plan: allocation and the handle
-    exchange happen once, later solves only bump the epoch."""
+    exchange happen once, later solves only bump the epoch.  A different plan evicts (and frees) the
+    cached blocks; `close_all()` runs at interpreter exit."""
 
     _cache: dict = {}
     _warned = False
+    MAX_CACHED = 2
 
     @classmethod
     def get(cls, plan: SlabPlan, d: int, group=None) -> "P2PComm":
         key = (plan.rank, plan.world, plan.own_lo, plan.own_hi, plan.g_lo, plan.g_hi, d)
         if key not in cls._cache:
+            # eviction is collective by construction: every rank builds the same sequence of plans
+            while len(cls._cache) >= cls.MAX_CACHED:
+                cls._cache.pop(next(iter(cls._cache))).close(group)
             cls._cache[key] = cls(plan, d, group)
         return cls._cache[key]
+
+    @classmethod
+    def close_all(cls) -> None:
+        for comm in list(cls._cache.values()):
+            comm.close(None, collective=False)
+        cls._cache.clear()
 
     def __init__(self, plan: SlabPlan, d: int, group=None):
         import ctypes
@@ -359,7 +401,22 @@ class P2PComm:
             return
         dist.barrier(group=group)  # every block is mapped everywhere before anyone writes
 
-    def descriptor(self) -> "_lib.PeerComm":
+    def close(self, group=None, collective: bool = True) -> None:
+        """Unmap the peers' blocks and free the own one.  Collective (barrier first: nobody may still be
+        writing into a block that is about to disappear) unless called at interpreter exit."""
+        if collective and dist.is_available() and dist.is_initialized():
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+        for r, p in enumerate(self.ptrs):
+            if p is not None and r != self.plan.rank:
+                self.lib.fea_comm_ipc_close(p)
+        self.ptrs = []
+        if self.own is not None:
+            self.lib.fea_comm_free(self.own)
+            self.own = None
+        self.available = False
+
+    def descriptor(self, boundary=(0, 0), algo: int = -1, max_rank_dof: int = 0) -> "_lib.PeerComm":
         pl = self.plan
         self.epoch += 1
         c = _lib.PeerComm()
@@ -376,11 +433,35 @@ class P2PComm:
             peer, lo, hi = pl.send_up
             c.send_upper_first, c.send_upper_count, c.send_upper_dst = lo - pl.own_lo, hi - lo, lo - self.g_los[peer]
         c.epoch = self.epoch
+        c.boundary_lower_nodes, c.boundary_upper_nodes = int(boundary[0]), int(boundary[1])
+        c.algo, c.max_rank_dof = int(algo), int(max_rank_dof)
         return c
 
 
-def p2p_pcg(K, plan: SlabPlan, b_owned: torch.Tensor, dinv_owned: torch.Tensor, tol: float, max_iter: int, group=None):
-    """Distributed Jacobi-PCG through fea_pcg_solve_p2p (NVLink peer memory, no NCCL per iteration)."""
+import atexit  # noqa: E402
+
+atexit.register(P2PComm.close_all)
+
+
+def boundary_nodes(node_rowptr: torch.Tensor, node_colidx: torch.Tensor, offset: int, n_owned: int):
+    """(lower, upper): owned nodes [0, lower) couple to a lower-halo node (local id < offset), the
+    last `upper` owned nodes to an upper-halo node (local id >= offset + n_owned).  Column lists are
+    sorted, so the first / last entry of a node's list decides.  The SpMV sweeps the rows in between
+    first and waits for the neighbours' halo only then (fea_peer_comm, include/fea_b200.h)."""
+    rp = node_rowptr[offset:offset + n_owned + 1].long()
+    first = node_colidx[rp[:-1]]
+    last = node_colidx[rp[1:] - 1]
+    lo_idx = torch.nonzero(first < offset).flatten()
+    up_idx = torch.nonzero(last >= offset + n_owned).flatten()
+    lower = int(lo_idx.max()) + 1 if lo_idx.numel() else 0
+    upper = n_owned - int(up_idx.min()) if up_idx.numel() else 0
+    return lower, upper
+
+
+def p2p_pcg(K, plan: SlabPlan, b_owned: torch.Tensor, dinv_owned: torch.Tensor, tol: float, max_iter: int, group=None,
+            history: bool = False, max_rank_dof: int = 0, algo: int = -1):
+    """Distributed Jacobi-PCG through fea_pcg_solve_p2p (NVLink peer memory, no NCCL per iteration).
+    Returns (x_owned, DistInfo, history or None)."""
     import ctypes
 
     from . import core
@@ -388,30 +469,78 @@ def p2p_pcg(K, plan: SlabPlan, b_owned: torch.Tensor, dinv_owned: torch.Tensor, 
     lib = _lib.load()
     d = K.dof_per_node
     comm = P2PComm.get(plan, d, group)
-    desc = comm.descriptor()
+    pt = K.pattern
+    desc = comm.descriptor(boundary_nodes(pt.node_rowptr, pt.node_colidx, plan.offset, plan.n_owned), algo=algo,
+                           max_rank_dof=max_rank_dof)
     n = plan.n_owned * d
     x = torch.empty(n, dtype=torch.float64, device=b_owned.device)
     ws_bytes = lib.fea_pcg_workspace(n)
     work = torch.empty(ws_bytes, dtype=torch.uint8, device=b_owned.device)
-    rowptr_owned = K.pattern.node_rowptr[plan.offset:]
+    hist = torch.zeros(max_iter, dtype=torch.float64, device=b_owned.device) if history else None
+    rowptr_owned = pt.node_rowptr[plan.offset:]
     res = _lib.PcgResult()
-    pt = K.pattern
+    # The first exchange of the solve is the only point where the ranks meet with host-side skew (each
+    # one sliced, copied and assembled its slab on its own); meet on the host first, so that the
+    # in-kernel spins only ever see device-side skew.
+    torch.cuda.synchronize()
+    dist.barrier(group=group)
     _lib.check(lib.fea_pcg_solve_p2p(plan.n_owned, d, rowptr_owned.data_ptr(), pt.node_colidx.data_ptr(),
                                      K.values.data_ptr(), pt.max_coupled, dinv_owned.data_ptr(), b_owned.data_ptr(),
                                      x.data_ptr(), float(tol), int(max_iter), work.data_ptr(), ws_bytes,
+                                     None if hist is None else hist.data_ptr(),
                                      ctypes.byref(desc), ctypes.byref(res), core._stream()), "fea_pcg_solve_p2p")
-    if res.status == _lib.FEA_ERR_PEER:
-        raise _lib.FeaLibraryError("fea_pcg_solve_p2p: a peer rank never delivered its halo / partial sum")
-    return x, DistInfo(res.iterations, res.rel_residual, res.status, res.bnorm)
+    return (x, DistInfo(res.iterations, res.rel_residual, res.status, res.bnorm),
+            hist[:res.iterations].cpu().numpy() if history else None)
 
 
-def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan, tol=1e-12, max_iter=None,
-                    group=None):
-    """This rank's share of solve(nodes, elements, constraints, forces) (cubebeam.py:79-108).
-    All arguments are the GLOBAL host arrays (each rank slices its slab).  Returns
-    (u_owned (n_owned,3) device, reactions_owned device, DistInfo, BlockCSR)."""
+# ------------------------------------------------------------------------------------------------
+# slab inputs on the device, slab solve, gather
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SlabInputs:
+    """This rank's slab of the global mesh, resident on its GPU."""
+    plan: SlabPlan
+    nodes: torch.Tensor        # (n_local, 3) f64, local node range [g_lo, g_hi)
+    elements: torch.Tensor     # (m, npe) int32, local node ids, ascending global element order
+    fixed: torch.Tensor        # (3 n_local,) uint8
+    loads_owned: torch.Tensor  # (3 n_owned,) f64
+    n_nodes_global: int
+    h2d_bytes: int
+
+
+def upload_slab(nodes, elements, constraints, forces, plan: SlabPlan) -> SlabInputs:
+    """Slice this rank's slab out of the GLOBAL host arrays and copy it to the device."""
     from . import core
 
+    g_lo, g_hi = plan.g_lo, plan.g_hi
+    nodes = np.asarray(nodes)
+    elements = np.asarray(elements)
+    nodes_h = np.ascontiguousarray(nodes[g_lo:g_hi], dtype=np.float64)
+    nodes_d = core.to_device(nodes_h, torch.float64)
+    ids = plan.element_ids
+    if ids.size and int(ids[-1]) - int(ids[0]) + 1 == ids.size:
+        # slabs of a layer-major mesh own a contiguous element range: a view, shifted on the device
+        el_h = np.ascontiguousarray(elements[int(ids[0]):int(ids[-1]) + 1])
+        elements_d = (core.to_device(el_h, torch.int64) - g_lo).to(torch.int32)
+    else:
+        el_h = np.ascontiguousarray(elements[ids] - g_lo)
+        elements_d = core.to_device(el_h, torch.int32)
+    cons_h = np.ascontiguousarray(np.asarray(constraints)[g_lo:g_hi])
+    fixed = core._fixed_mask(cons_h, 3 * plan.n_local)
+    loads_h = np.ascontiguousarray(np.asarray(forces)[plan.own_lo:plan.own_hi], dtype=np.float64)
+    loads = core.to_device(loads_h, torch.float64).reshape(-1)
+    h2d = int(nodes_h.nbytes + el_h.nbytes + cons_h.size + loads_h.nbytes)  # constraints travel as one byte per DOF
+    return SlabInputs(plan, nodes_d, elements_d, fixed, loads, int(nodes.shape[0]), h2d)
+
+
+def solve_slab(inp: SlabInputs, E: float, nu: float, tol: float = 1e-12, max_iter: int | None = None, group=None,
+               history: bool = False, raise_on_failure: bool = True, max_rank_dof: int = 0):
+    """Symbolic pass + assembly + distributed Jacobi-PCG + reactions on device-resident slab inputs.
+    Returns (u_owned (n_owned, 3), reactions_owned (n_owned, 3), DistInfo, BlockCSR); info.history is
+    the world residual history when `history`."""
+    from . import core
+
+    plan = inp.plan
     prof = STAGE_PROFILE if STAGE_PROFILE.get("enabled") else None
 
     def mark(name, t0):
@@ -423,26 +552,14 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
         return t1
 
     t = time.perf_counter()
-    g_lo, g_hi = plan.g_lo, plan.g_hi
-    nodes_d = core.to_device(np.ascontiguousarray(nodes[g_lo:g_hi]), torch.float64)
-    ids = plan.element_ids
-    if ids.size and int(ids[-1]) - int(ids[0]) + 1 == ids.size:
-        # slabs of a layer-major mesh own a contiguous element range: a view, shifted on the device
-        el_view = np.ascontiguousarray(np.asarray(elements)[int(ids[0]):int(ids[-1]) + 1])
-        elements_d = (core.to_device(el_view, torch.int64) - g_lo).to(torch.int32)
-    else:
-        elements_d = core.to_device(np.ascontiguousarray(np.asarray(elements)[ids] - g_lo), torch.int32)
-    fixed = core._fixed_mask(np.ascontiguousarray(np.asarray(constraints)[g_lo:g_hi]), 3 * plan.n_local)
-    t = mark("slice_h2d", t)
-    K = core.assemble_hex8(nodes_d, elements_d, E, nu, fixed=fixed)
+    K = core.assemble_hex8(inp.nodes, inp.elements, E, nu, fixed=inp.fixed)
     lo, hi = 3 * plan.offset, 3 * (plan.offset + plan.n_owned)
     dinv_owned = K.dinv[lo:hi].contiguous()
-    b_owned = core.to_device(np.ascontiguousarray(np.asarray(forces)[plan.own_lo:plan.own_hi]),
-                             torch.float64).reshape(-1)
     t = mark("symbolic_assembly", t)
     ops = GpuOps(K, plan)
     if max_iter is None:
-        max_iter = 10 * 3 * int(np.asarray(nodes).shape[0])
+        max_iter = 10 * 3 * inp.n_nodes_global
+    max_iter = int(min(max_iter, 2**31 - 1))
     # NVLink peer-memory solver by default; FEA_DIST_COMM=nccl selects the torch.distributed loop, which
     # is also what every rank falls back to (together) when CUDA IPC cannot be set up between the ranks
     use_p2p = plan.world > 1 and os.environ.get("FEA_DIST_COMM", "p2p") == "p2p"
@@ -453,11 +570,17 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
             P2PComm._warned = True
         use_p2p = False
     SOLVER_USED["kind"] = "p2p" if use_p2p else ("nccl" if plan.world > 1 else "single")
+    hist = None
     if use_p2p:
-        x, info = p2p_pcg(K, plan, b_owned, dinv_owned, tol, max_iter, group=group)
+        x, info, hist = p2p_pcg(K, plan, inp.loads_owned, dinv_owned, tol, max_iter, group=group, history=history,
+                                max_rank_dof=max_rank_dof)
     else:
-        x, info = distributed_pcg(ops, plan, 3, b_owned, dinv_owned, tol=tol, max_iter=max_iter, group=group)
+        x, info = distributed_pcg(ops, plan, 3, inp.loads_owned, dinv_owned, tol=tol, max_iter=max_iter, group=group)
+    info.history = hist
     t = mark("pcg", t)
+    if raise_on_failure and info.status != _lib.FEA_OK:
+        # every rank holds the same status (the convergence decisions are bitwise identical): all raise
+        _lib.raise_for_status(np.array([info.status, 0x7FFFFFFF - info.iterations]))
     # reactions: K_full u on the owned rows needs u on the halo
     u_ext = torch.zeros(3 * plan.n_local, dtype=torch.float64, device=x.device)
     u_ext[lo:hi] = x
@@ -468,119 +591,130 @@ def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan,
     return x.reshape(-1, 3), reactions.reshape(-1, 3), info, K
 
 
-# which distributed solver the last solve_hex8_slab call used ("p2p" | "nccl" | "single")
+def solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan: SlabPlan, tol=1e-12, max_iter=None,
+                    group=None, **kw):
+    """This rank's share of solve(nodes, elements, constraints, forces) (cubebeam.py:79-108) from the
+    GLOBAL host arrays: slice + H2D (upload_slab), then solve_slab.  Results stay on the device."""
+    t = time.perf_counter()
+    inp = upload_slab(nodes, elements, constraints, forces, plan)
+    if STAGE_PROFILE.get("enabled"):
+        torch.cuda.synchronize()
+        STAGE_PROFILE["slice_h2d"] = STAGE_PROFILE.get("slice_h2d", 0.0) + (time.perf_counter() - t) * 1e3
+    return solve_slab(inp, E, nu, tol=tol, max_iter=max_iter, group=group, **kw)
+
+
+def gather_rows(plan: SlabPlan, cuts, owned: torch.Tensor, group=None, dst: int = 0):
+    """`owned` is (k, n_owned, ...): concatenate every rank's owned nodes along axis 1 on rank `dst`
+    (None elsewhere).  Slab sizes are uneven, hence grouped send / recv instead of a gather."""
+    world, rank = plan.world, plan.rank
+    if world == 1:
+        return owned
+    if rank == dst:
+        n_total = int(cuts[-1])
+        full = torch.empty((owned.shape[0], n_total) + tuple(owned.shape[2:]), dtype=owned.dtype, device=owned.device)
+        full[:, plan.own_lo:plan.own_hi] = owned
+        # one contiguous staging buffer per peer (a column slice of `full` is strided)
+        bufs, ops = {}, []
+        for r in range(world):
+            if r == dst:
+                continue
+            lo, hi = int(cuts[r]), int(cuts[r + 1])
+            bufs[r] = torch.empty((owned.shape[0], hi - lo) + tuple(owned.shape[2:]), dtype=owned.dtype,
+                                  device=owned.device)
+            ops.append(dist.P2POp(dist.irecv, bufs[r], r, group=group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for r, buf in bufs.items():
+            full[:, int(cuts[r]):int(cuts[r + 1])] = buf
+        return full
+    for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, owned.contiguous(), dst, group=group)]):
+        req.wait()
+    return None
+
+
+def default_cuts(n_nodes: int, world: int) -> np.ndarray:
+    """Node-balanced slab cuts (not aligned to mesh layers: 401 layers on 8 ranks would leave one rank
+    with 51 layers against 50, and the slowest rank sets the pace of every iteration)."""
+    return node_cuts(n_nodes, world)
+
+
+def solve_hex8(nodes, elements, constraints, forces, E: float, nu: float, tol: float = 1e-12,
+               max_iter: int | None = None, group=None, cuts=None, plan: SlabPlan | None = None,
+               return_info: bool = False, all_ranks: bool = False):
+    """The reference's solve(nodes, elements, constraints, forces) -> (displacements, forces)
+    (cubebeam.py:79-108) on every GPU of the process group: a COLLECTIVE call, every rank passes the
+    same global host arrays.  Each rank copies only its slab of node layers to its GPU, assembles it
+    and takes part in one distributed Jacobi-PCG; the owned rows of u and of K_full u are gathered on
+    rank 0 over NVLink and copied to the host there.  Rank 0 returns the host arrays (N, 3) like the
+    reference; the other ranks return (None, None) unless `all_ranks` (then every rank receives a copy).
+    Raises like the single-GPU path, on every rank (ValueError for an inverted element,
+    numpy.linalg.LinAlgError for a singular / non-converging reduced system)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nodes_a = np.asarray(nodes)
+    n_nodes = int(nodes_a.shape[0])
+    if cuts is None:
+        cuts = default_cuts(n_nodes, world)
+    if plan is None:
+        plan = plan_slab(np.asarray(elements), cuts, rank)
+    inp = upload_slab(nodes_a, elements, constraints, forces, plan)
+    max_rank_dof = 3 * int(np.diff(cuts).max())
+    u, react, info, K = solve_slab(inp, E, nu, tol=tol, max_iter=max_iter, group=group, max_rank_dof=max_rank_dof)
+    t = time.perf_counter()
+    both = torch.stack([u.reshape(-1), react.reshape(-1)]).reshape(2, plan.n_owned, 3)
+    full = gather_rows(plan, cuts, both, group=group)
+    if all_ranks:
+        if full is None:
+            full = torch.empty((2, n_nodes, 3), dtype=torch.float64, device=u.device)
+        dist.broadcast(full, src=0, group=group)
+    out = (None, None)
+    if full is not None:
+        host = full.cpu().numpy()
+        out = (host[0].reshape(nodes_a.shape), host[1].reshape(nodes_a.shape))
+    if STAGE_PROFILE.get("enabled"):
+        torch.cuda.synchronize()
+        STAGE_PROFILE["gather_d2h"] = STAGE_PROFILE.get("gather_d2h", 0.0) + (time.perf_counter() - t) * 1e3
+    if return_info:
+        return out[0], out[1], info, K
+    return out
+
+
+def solve_hex8_or_none(nodes, elements, constraints, forces, E, nu, group=None, **kw):
+    """solve_hex8, or None on EVERY rank when the mesh cannot be cut into `world` slabs (a slab thinner
+    than the mesh bandwidth, or a node numbering that is not layer-major): the caller then solves on one
+    GPU per rank.  The decision is collective (all-reduced), so no rank is left waiting."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_nodes = int(np.asarray(nodes).shape[0])
+    cuts = default_cuts(n_nodes, world)
+    ok, plan = 1, None
+    try:
+        if int(np.diff(cuts).min()) < 1:
+            raise ValueError("fewer nodes than ranks")
+        plan = plan_slab(np.asarray(elements), cuts, rank)
+    except ValueError:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag) == 0:
+        return None
+    return solve_hex8(nodes, elements, constraints, forces, E, nu, group=group, cuts=cuts, plan=plan, **kw)
+
+
+def active_world(group=None) -> int:
+    """World size of the initialised NCCL process group (1 if there is none): model.solve_hex8 routes
+    through solve_hex8 above when it is > 1."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    try:
+        if dist.get_backend(group) != "nccl":
+            return 1
+    except Exception:  # noqa: BLE001
+        return 1
+    return dist.get_world_size(group)
+
+
+# which distributed solver the last solve_slab call used ("p2p" | "nccl" | "single")
 SOLVER_USED: dict = {"kind": None}
 
-# stage timings of solve_hex8_slab (ms, accumulated; each stage ends with a device synchronise) when
+# stage timings of the slab solve (ms, accumulated; each stage ends with a device synchronise) when
 # STAGE_PROFILE["enabled"] is set -- bench.py switches it on for ONE extra untimed step.
 STAGE_PROFILE: dict = {"enabled": False}
-
-
-# ------------------------------------------------------------------------------------------------
-# bench.py entry for N > 1 (launched by torchrun, one rank per GPU)
-# ------------------------------------------------------------------------------------------------
-def bench_entry(args, A, b, tol, E, nu, measured_peaks, ClockSampler, cpu_sample):
-    from . import core, cubebeam
-
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _lib.load()
-    nodes, elements, constraints, forces = cubebeam.cantilever_case(A, b)
-    n_free = int((constraints == 0).sum())
-    cuts = node_cuts(nodes.shape[0], world, layer=(b + 1) ** 2)
-    plan = plan_slab(elements, cuts, rank)
-
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    out = {}
-
-    def step():
-        u, react, info, K = solve_hex8_slab(nodes, elements, constraints, forces, E, nu, plan, tol=tol)
-        out.update(info=info, K=K)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    lib.fea_profile_enable(1)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms)
-    prof = (4 * __import__("ctypes").c_double)()
-    lib.fea_profile_read(prof)
-    # one more, untimed, step with a synchronise after every stage: where a step's time goes
-    STAGE_PROFILE.clear()
-    STAGE_PROFILE["enabled"] = True
-    barrier()
-    step()
-    STAGE_PROFILE["enabled"] = False
-    stages = {k: round(v, 3) for k, v in STAGE_PROFILE.items() if k != "enabled"}
-    info, K = out["info"], out["K"]
-    # SpMV kernel alone on this rank's slab (CUDA events, after the timed region)
-    p_ext = torch.randn(3 * plan.n_local, dtype=torch.float64, device="cuda")
-    y = torch.empty(3 * plan.n_owned, dtype=torch.float64, device="cuda")
-    ops = GpuOps(K, plan)
-    for _ in range(3):
-        ops.matvec_owned(p_ext, y)
-    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    reps = 20
-    for _ in range(reps):
-        ops.matvec_owned(p_ext, y)
-    c.record()
-    torch.cuda.synchronize()
-    spmv_ms = a.elapsed_time(c) / reps
-    own_nnz = 9 * int(K.pattern.node_rowptr[plan.offset + plan.n_owned] - K.pattern.node_rowptr[plan.offset])
-    alg = 12 * own_nnz + 20 * 3 * plan.n_owned
-    stats = torch.tensor([spmv_ms, alg / (spmv_ms / 1e3) / 1e9], dtype=torch.float64, device="cuda")
-    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    agg = torch.tensor([alg / (spmv_ms / 1e3) / 1e9], dtype=torch.float64, device="cuda")
-    dist.all_reduce(agg)
-    if rank == 0:
-        hbm_peak, peak_src = measured_peaks()
-        per_gpu = float(agg) / world
-        line = {
-            "metric": "hex8 beam solved DOF/s", "value": n_free / (ms_per_step / 1e3), "unit": "solved DOF/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"cubebeam hex8 cantilever {A}x{b}x{b}", "dof": int(nodes.size),
-                       "free_dof": n_free, "elements": int(elements.shape[0]), "tol": tol,
-                       "pcg_iterations": info.iterations, "rel_residual": info.rel_residual,
-                       "preconditioner": "jacobi",
-                       "parallelism": (f"{world} z-slabs, NVLink peer-memory exchange fused into the three PCG "
-                                       "kernels of the solver's CUDA graph (no NCCL per iteration)"
-                                       if SOLVER_USED["kind"] == "p2p" else
-                                       f"{world} z-slabs, NCCL halo send/recv + all-reduced dots"),
-                       "l2": "per-rank CSR slab larger than L2 for N <= 8; no flush"},
-            "roofline": {"kernel": "spmv_tma_kernel<3,2> on the rank's slab (timed alone after the steps)", "bound": "hbm",
-                         "achieved": per_gpu, "peak": hbm_peak, "unit": "GB/s", "frac": per_gpu / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "aggregate_gb_per_s": float(agg),
-                         "slowest_rank_ms": float(stats[0])},
-            "stages_ms_rank0": stages,
-            "cpu_baseline": None,
-            "e2e": {"value": n_free / (ms_per_step / 1e3), "unit": "solved DOF/s",
-                    "h2d_bytes_per_step": int(nodes[plan.g_lo:plan.g_hi].nbytes + plan.element_ids.size * 64
-                                              + 2 * forces[plan.own_lo:plan.own_hi].nbytes),
-                    "d2h_bytes_per_step": 256,
-                    "note": "every step starts from the host mesh arrays: slab slicing, H2D, symbolic, assembly, "
-                            "distributed PCG, reactions are all inside the timed region; results stay sharded on the GPUs"},
-            "clocks": clocks, "gpu_launches": int(prof[0]) // max(args.steps, 1),
-        }
-        print(json.dumps(line))
-    dist.barrier()
-    dist.destroy_process_group()

@@ -20,7 +20,21 @@ def solve_hex8(nodes, elements, constraints, forces, E: float = E_DEFAULT, nu: f
     and return the nodal forces K_full u (applied loads on free DOF, reactions on constrained DOF).
     Inputs are not modified.  ValueError for an inverted element (utils.py:212-215),
     numpy.linalg.LinAlgError for a singular reduced system (what np.linalg.solve raises).
+
+    Under an initialised NCCL process group with more than one rank (torchrun, one rank per GPU) the
+    call is COLLECTIVE: every rank passes the same host arrays, the mesh is split into slabs of node
+    layers, and rank 0 returns the full host arrays while the other ranks return (None, None)
+    (fea_b200/dist.py:solve_hex8).  FEA_DIST=0 keeps every rank on its own single-GPU solve.
     """
+    import os
+
+    from . import dist as fdist
+
+    if fdist.active_world() > 1 and os.environ.get("FEA_DIST", "1") != "0" and not history:
+        res = fdist.solve_hex8_or_none(nodes, elements, constraints, forces, E, nu, tol=tol, max_iter=max_iter,
+                                       return_info=return_info)
+        if res is not None:
+            return res
     nodes_d = core.to_device(nodes, torch.float64)
     if nodes_d.ndim != 2 or nodes_d.shape[1] != 3:
         raise ValueError("nodes must be (N, 3)")

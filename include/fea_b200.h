@@ -39,7 +39,9 @@ enum {
   FEA_ERR_MAXITER = 5,   /* PCG hit max_iter before the tolerance */
   FEA_ERR_WORKSPACE = 6, /* caller workspace too small */
   FEA_ERR_DEGENERATE = 7, /* zero-length truss member */
-  FEA_ERR_PEER = 8        /* multi-GPU: a peer rank never delivered its halo / partial sum */
+  FEA_ERR_PEER = 8,       /* multi-GPU: a peer rank never delivered its halo / partial sum */
+  FEA_ERR_STAGNATION = 9  /* PCG residual stopped improving: singular (under-constrained) reduced system
+                             with an inconsistent load (cubebeam.py:98 -> LinAlgError) */
 };
 
 /* Library / build identification ("fea_b200 <version> sm_100a"). */
@@ -249,7 +251,25 @@ typedef struct {
   int64_t send_lower_first, send_lower_count, send_lower_dst;
   int64_t send_upper_first, send_upper_count, send_upper_dst;
   int64_t epoch;                   /* distinct for every solve that reuses the blocks (same on all ranks) */
+  /* Owned nodes [0, boundary_lower_nodes) couple to lower-halo nodes and the last boundary_upper_nodes
+   * owned nodes to upper-halo nodes: the SpMV sweeps the other rows first and only then looks at the
+   * neighbours' halo tags (the exchange hides behind the interior of the slab). */
+  int64_t boundary_lower_nodes, boundary_upper_nodes;
+  /* PCG recurrence, identical on every rank (checked in the first exchange): 0 classical, 1 single
+   * reduction (Chronopoulos-Gear), -1 = choose from max_rank_dof (the LARGEST owned DOF count of any
+   * rank -- a rank-invariant quantity; slabs are uneven). */
+  int32_t algo, reserved;
+  int64_t max_rank_dof;
 } fea_peer_comm;
+
+/* Host-side partition helper: one multi-threaded pass over the GLOBAL connectivity in HOST memory
+ * (int64 or int32 node ids, index_bytes = 8 | 4).  For each node range r = [ranges_host[2r],
+ * ranges_host[2r+1]) it reports, in out_host[5r..5r+5): the number of elements with at least one
+ * node in the range, the first and last such element id (-1 if none), and the smallest / largest
+ * node id those elements reference.  A rank's slab = its owned range; its halo = [min, max] beyond
+ * it; what it sends = the neighbours' ranges scanned the same way (fea_b200/dist.py:plan_slab). */
+int fea_slab_scan(const void* elements_host, int32_t index_bytes, int64_t n_elem, int32_t nodes_per_elem,
+                  const int64_t* ranges_host, int32_t n_ranges, int64_t* out_host);
 
 size_t fea_comm_bytes(int64_t n_local_dof);
 int fea_comm_alloc(size_t bytes, void** out);  /* cudaMalloc + zero */
@@ -260,12 +280,14 @@ int fea_comm_ipc_close(void* ptr);
 
 /* Arguments as fea_pcg_solve, restricted to this rank's owned rows: node_rowptr_owned points at
  * the first owned node's entry of the slab's node_rowptr (entries stay absolute), dinv / b / x have
- * n_owned_nodes * dof_per_node entries.  Synchronises; identical result on every rank.
- * result_host->status may also be FEA_ERR_PEER (a peer never arrived). */
+ * n_owned_nodes * dof_per_node entries.  history as in fea_pcg_solve (every rank records the same
+ * world residuals).  Synchronises; identical result on every rank.
+ * result_host->status may also be FEA_ERR_PEER (a peer never arrived, or the ranks disagree on the
+ * recurrence). */
 int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t dof_per_node, const int32_t* node_rowptr_owned,
                       const int32_t* node_colidx, const double* values, int32_t max_coupled,
                       const double* dinv, const double* b, double* x, double tol, int32_t max_iter,
-                      void* work, size_t work_bytes, const fea_peer_comm* comm,
+                      void* work, size_t work_bytes, double* history, const fea_peer_comm* comm,
                       fea_pcg_result* result_host, void* stream);
 
 /* Batched multi-RHS Jacobi-PCG (BASELINE config 5): n_rhs <= 256 independent systems sharing K,

@@ -35,6 +35,8 @@ def load():
         lib = ctypes.CDLL(build())
         P, i64, f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double
         lib.fea_c_threads.restype = ctypes.c_int
+        lib.fea_c_set_threads.restype = None
+        lib.fea_c_set_threads.argtypes = [ctypes.c_int]
         lib.fea_c_hex8_ke.restype = ctypes.c_int
         lib.fea_c_hex8_ke.argtypes = [P, f64, f64, P]
         lib.fea_c_hex8_ke_batch.restype = i64
@@ -45,12 +47,22 @@ def load():
         lib.fea_c_spmv.argtypes = [i64, P, P, P, P, P]
         lib.fea_c_jacobi_pcg.restype = i64
         lib.fea_c_jacobi_pcg.argtypes = [i64, P, P, P, P, P, f64, i64, P]
+        lib.fea_c_reduce_csr.restype = None
+        lib.fea_c_reduce_csr.argtypes = [i64, P, P, P, P, P, P, P]
+        lib.fea_c_expand_pattern.restype = None
+        lib.fea_c_expand_pattern.argtypes = [i64, ctypes.c_int32, P, P, P, P]
         _lib = lib
     return _lib
 
 
 def threads() -> int:
     return int(load().fea_c_threads())
+
+
+def set_threads(n: int) -> int:
+    """Pin the OpenMP team size (whatever OMP_NUM_THREADS the launcher exported); returns it."""
+    load().fea_c_set_threads(int(n))
+    return threads()
 
 
 def _ptr(a: np.ndarray) -> int:
@@ -80,15 +92,36 @@ def dof_pattern(elements, n_nodes: int, d: int):
     A = sp.coo_matrix((np.ones(rows.size, dtype=np.int8), (rows, cols)), shape=(n_nodes, n_nodes)).tocsr()
     A.sum_duplicates()
     A.sort_indices()
-    cnt = np.diff(A.indptr).astype(np.int64)
-    seg = (d * A.indices.astype(np.int64)[:, None] + np.arange(d)).ravel()  # one DOF row per node, concatenated
-    seg_start = d * A.indptr[:-1].astype(np.int64)
-    row_len = np.repeat(d * cnt, d)            # length of every DOF row
-    row_src = np.repeat(seg_start, d)          # where its columns start in `seg`
-    indptr = np.zeros(d * n_nodes + 1, dtype=np.int64)
-    np.cumsum(row_len, out=indptr[1:])
-    pos = np.arange(indptr[-1]) - np.repeat(indptr[:-1], row_len) + np.repeat(row_src, row_len)
-    return indptr.astype(np.int32), seg[pos].astype(np.int32)
+    if d * d * A.nnz >= 2**31:
+        raise ValueError("pattern does not fit int32")
+    indptr_n = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    indices_n = np.ascontiguousarray(A.indices, dtype=np.int32)
+    indptr = np.empty(d * n_nodes + 1, dtype=np.int32)
+    indices = np.empty(d * d * A.nnz, dtype=np.int32)
+    load().fea_c_expand_pattern(n_nodes, d, _ptr(indptr_n), _ptr(indices_n), _ptr(indptr), _ptr(indices))
+    return indptr, indices
+
+
+def reduce_csr(K: sp.csr_matrix, free: np.ndarray) -> sp.csr_matrix:
+    """`K[np.ix_(free, free)]` (cubebeam.py:92-96) without scipy's fancy-indexing temporaries:
+    two parallel passes over the rows (count, fill).  `free` ascending."""
+    n = K.shape[0]
+    free = np.asarray(free, dtype=np.int64)
+    dof_map = np.full(n, -1, dtype=np.int32)
+    dof_map[free] = np.arange(free.size, dtype=np.int32)
+    indptr = np.ascontiguousarray(K.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(K.indices, dtype=np.int32)
+    data = np.ascontiguousarray(K.data, dtype=np.float64)
+    out_indptr = np.zeros(free.size + 1, dtype=np.int64)
+    lib = load()
+    lib.fea_c_reduce_csr(n, _ptr(indptr), _ptr(indices), _ptr(data), _ptr(dof_map), _ptr(out_indptr), None, None)
+    np.cumsum(out_indptr, out=out_indptr)
+    nnz = int(out_indptr[-1])
+    out_indices = np.empty(nnz, dtype=np.int32)
+    out_data = np.empty(nnz, dtype=np.float64)
+    lib.fea_c_reduce_csr(n, _ptr(indptr), _ptr(indices), _ptr(data), _ptr(dof_map), _ptr(out_indptr),
+                         _ptr(out_indices), _ptr(out_data))
+    return sp.csr_matrix((out_data, out_indices, out_indptr.astype(np.int32)), shape=(free.size, free.size))
 
 
 def assemble_hex8(nodes, elements, E: float, nu: float, pattern=None) -> sp.csr_matrix:

@@ -29,6 +29,16 @@ int fea_c_threads(void) {
 #endif
 }
 
+/* Pin the OpenMP team size (bench.py: torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm
+ * uses the host's cores whatever the launcher set). */
+void fea_c_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* Local node signs, bottom face CCW then top face CCW (utils.py:159-197, 351-353). */
 static const double SX[8] = {-1, +1, +1, -1, -1, +1, +1, -1};
 static const double SY[8] = {-1, -1, +1, +1, -1, -1, +1, +1};
@@ -231,4 +241,50 @@ int64_t fea_c_jacobi_pcg(int64_t n, const int32_t* indptr, const int32_t* indice
   free(ap);
   free(dinv);
   return it;
+}
+
+/* Constraint reduction `K[np.ix_(free, free)]` (cubebeam.py:92-96) on CSR, two passes.
+ * map[i] = rank of DOF i within `free` (ascending), or -1 for a constrained DOF.
+ * Pass 1 (out_indices == NULL): out_indptr[r + 1] = length of reduced row r; the caller turns the
+ * counts into offsets.  Pass 2: fills indices / data at those offsets. */
+void fea_c_reduce_csr(int64_t n, const int32_t* indptr, const int32_t* indices, const double* data,
+                      const int32_t* map, int64_t* out_indptr, int32_t* out_indices, double* out_data) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t r = map[i];
+    if (r < 0) continue;
+    if (out_indices == NULL) {
+      int64_t c = 0;
+      for (int64_t p = indptr[i]; p < indptr[i + 1]; ++p) c += map[indices[p]] >= 0;
+      out_indptr[r + 1] = c;
+    } else {
+      int64_t q = out_indptr[r];
+      for (int64_t p = indptr[i]; p < indptr[i + 1]; ++p) {
+        const int32_t c = map[indices[p]];
+        if (c >= 0) {
+          out_indices[q] = c;
+          out_data[q] = data[p];
+          ++q;
+        }
+      }
+    }
+  }
+}
+
+/* Expansion of a node-level CSR pattern (indptr_n, sorted indices_n) to d DOF per node: row d*i+a
+ * holds columns d*j+b, j over the node's list, b < d (DOF map d*node + component, cubebeam.py:86).
+ * out_indptr has d*n_nodes+1 entries, out_indices d*d*nnz_nodes. */
+void fea_c_expand_pattern(int64_t n_nodes, int32_t d, const int32_t* indptr_n, const int32_t* indices_n,
+                          int32_t* out_indptr, int32_t* out_indices) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    const int64_t lo = indptr_n[i], cnt = indptr_n[i + 1] - lo;
+    for (int32_t a = 0; a < d; ++a) {
+      const int64_t base = (int64_t)d * d * lo + (int64_t)a * d * cnt;
+      out_indptr[d * i + a] = (int32_t)base;
+      for (int64_t k = 0; k < cnt; ++k)
+        for (int32_t b = 0; b < d; ++b) out_indices[base + d * k + b] = d * indices_n[lo + k] + b;
+    }
+  }
+  out_indptr[d * n_nodes] = (int32_t)((int64_t)d * d * indptr_n[n_nodes]);
 }
