@@ -76,7 +76,25 @@ def config4():
         sum_reactions_y=f_out.reshape(-1, 3)[base, 1].sum(), threads=co.threads(), seconds=np.array(secs))
 
 
+def config5(n: int = 30):
+    """Config-5-shaped lattice truss at n = 30 (27,000 nodes, 78,300 free DOF, 64 load
+    cases): scipy's sparse LU of the reduced oracle matrix, every column.  Keeps a seeded row sample."""
+    import scipy.sparse.linalg as spla
+
+    nodes, members, k, cons, B = fo.lattice_truss_case(n, n_rhs=64)[:5]
+    K = fo.assemble_csr(members, fo.truss_ke_batched(nodes, members, k), nodes.shape[0], 3)
+    free = fo.free_dofs(cons)
+    t0 = time.perf_counter()
+    lu = spla.splu(K[free][:, free].tocsc())
+    X = np.zeros_like(B)
+    X[free] = lu.solve(B[free])
+    print(f"sparse LU of {free.size} DOF x 64 RHS: {time.perf_counter() - t0:.1f}s", flush=True)
+    rows = np.sort(np.random.default_rng(0).choice(B.shape[0], 4000, replace=False))
+    np.savez_compressed(os.path.join(OUT, "oracle_config5_n30.npz"), n=n, rows=rows, X_rows=X[rows],
+                        col_norms=np.linalg.norm(X, axis=0), col_max=np.abs(X).max(axis=0))
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "config3"
-    {"config3": config3, "config4": config4}[which]()
+    {"config3": config3, "config4": config4, "config5": config5}[which]()
     print("wrote", which)

@@ -1,6 +1,8 @@
 """GPU parity: the CUDA path (through the C ABI) against the oracle and the reference-generated
 golden fixtures.  Bars (BASELINE.json north_star): CSR pattern and DOF numbering bit-exact;
 Ke / K values within 1e-10 relative; displacements within 1e-8 relative at CG residual 1e-12."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -320,6 +322,32 @@ def test_pcg_zero_rhs_and_singular(mods):
         model.solve_hex8(nodes, elements, np.zeros_like(cons), forces, max_iter=2000)
 
 
+def test_pcg_stagnation_exit(mods):
+    """An under-constrained body with the DEFAULT max_iter (10 n): the residual stops improving and the
+    solve ends with FEA_ERR_STAGNATION -> LinAlgError after ~10 k iterations instead of 10 n."""
+    from fea_b200 import _lib
+
+    core = mods["core"]
+    nodes, elements, cons, forces = fo.cantilever_case(40, 8)  # 9,963 DOF: max_iter = 99,630
+    nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
+    b = core.to_device(forces, torch.float64).reshape(-1)
+    K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, fixed=core._fixed_mask(np.zeros_like(cons), nodes.size))
+    for algo in ("0", "1"):
+        os.environ["FEA_PCG_ALGO"] = algo
+        try:
+            _, info = core.pcg(K, b, raise_on_failure=False)
+        finally:
+            del os.environ["FEA_PCG_ALGO"]
+        assert info.status in (_lib.FEA_ERR_STAGNATION, _lib.FEA_ERR_BREAKDOWN)
+        assert info.iterations < 40_000
+    with pytest.raises(np.linalg.LinAlgError):
+        core.pcg(K, b)
+    # a constrained solve of the same mesh is untouched by the guard
+    Kc = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, fixed=core._fixed_mask(cons, nodes.size))
+    _, info = core.pcg(Kc, b)
+    assert info.status == 0 and info.rel_residual <= 1e-12
+
+
 # ---------------------------------------------------------------- end-to-end, reference surface
 def test_k5_cubebeam_shipped(mods, golden):
     g = golden("cubebeam.npz")
@@ -397,6 +425,27 @@ def test_truss_lattice_multi_rhs(mods):
     # single RHS through the same entry point
     u1 = T.solve_linear(nodes, members, k, cons, loads[:, 0].reshape(-1, 3))
     assert rel(u1.ravel(), X[:, 0]) < 1e-9
+
+
+def test_config5_n30_converged_vs_sparse_lu(mods, golden):
+    """Config-5-shaped lattice truss at n = 30 (27,000 nodes, 78,300 free DOF, 64 load cases), batched
+    PCG run to CONVERGENCE on every column, against scipy's sparse LU of the oracle's reduced matrix
+    (recorded by oracle/make_golden_large.py config5: a seeded 4000-row sample of X, all 64 columns, and
+    the column norms of the full solution)."""
+    T = mods["truss"]
+    g = golden("oracle_config5_n30.npz")
+    n = int(g["n"])
+    nodes, members, k, cons, loads = T.lattice_truss(n, n_rhs=64)
+    on, om, ok_, oc, ol = fo.lattice_truss_case(n, n_rhs=64)[:5]  # the product's generator == the oracle's
+    assert np.array_equal(nodes, on) and np.array_equal(members, om) and np.array_equal(k, ok_)
+    assert np.array_equal(loads, ol)
+    X, K, info = T.solve_linear(nodes, members, k, cons, loads, return_matrix=True)
+    assert info.status == 0 and info.rel_residual <= 1e-12 and len(info.history) == 64
+    X = X if isinstance(X, np.ndarray) else X.cpu().numpy()
+    scale = g["col_max"][None, :]
+    assert (np.abs(X[g["rows"]] - g["X_rows"]) / scale).max() < U_RTOL
+    assert np.abs(np.linalg.norm(X, axis=0) / g["col_norms"] - 1.0).max() < U_RTOL
+    assert np.all(X[cons.ravel() != 0] == 0.0)
 
 
 def test_spmm_and_multi_rhs_wide_rows_and_odd_widths(mods):
@@ -520,6 +569,109 @@ def test_config3_full_size_properties(mods):
     assert 0.9 < w_tip / (total * 1.0**3 / (8 * EI)) < 1.15  # uniformly distributed load along z
 
 
+def test_config3_full_vs_oracle(mods, golden):
+    """BASELINE config 3 IN FULL against the oracle (tests/golden/oracle_config3.npz, written by
+    oracle/make_golden_large.py: the C twin's Jacobi-PCG to 1e-12 AND scipy's sparse LU of the same
+    reduced system): u within 1e-8 of both, same iteration count to a few, same reaction sum."""
+    from fea_b200 import model
+
+    g = golden("oracle_config3.npz")
+    C = mods["cubebeam"]
+    nodes, elements, cons, forces = C.cantilever_case(int(g["A"]), int(g["b"]))
+    u, f, info, K = model.solve_hex8(nodes, elements, cons, forces, return_info=True)
+    assert info.status == 0 and info.rel_residual <= 1e-12
+    assert rel(u.ravel(), g["u_pcg"]) < U_RTOL
+    assert rel(u.ravel(), g["u_direct"]) < U_RTOL
+    assert abs(info.iterations - int(g["iterations"])) <= 25  # rounding noise in K moves the count by a few
+    ry = f[nodes[:, 2] == 0][:, 1].sum()
+    assert abs(ry - float(g["sum_reactions_y"])) < 1e-8 * abs(ry)
+
+
+def test_config4_slab_vs_oracle_pcg(mods):
+    """A config-4-shaped slab (50x80x80: 1,003,833 DOF, nnz 79.3 M) against the oracle's own Jacobi-PCG
+    (oracle/fea_oracle_c.c on the host cores, run here): K values 1e-10, u 1e-8, iteration count."""
+    from fea_b200 import model
+    from oracle import c_oracle as co
+
+    C = mods["cubebeam"]
+    nodes, elements, cons, forces = C.cantilever_case(50, 80, length=0.125)
+    assert nodes.size > 1_000_000
+    u, f, info, K = model.solve_hex8(nodes, elements, cons, forces, return_info=True)
+    co.set_threads(len(os.sched_getaffinity(0)))
+    Ko = co.assemble_hex8(nodes, elements, fo.E_HEX, fo.NU_HEX)
+    rowptr, colidx = (t.cpu().numpy() for t in K.pattern.csr(3))
+    assert np.array_equal(rowptr, Ko.indptr) and np.array_equal(colidx, Ko.indices)
+    assert rel(K.values.cpu().numpy(), Ko.data) < KE_RTOL
+    free = fo.free_dofs(cons)
+    uf, it, relres = co.jacobi_pcg(co.reduce_csr(Ko, free), forces.flatten()[free], tol=1e-12)
+    uo = np.zeros(nodes.size)
+    uo[free] = uf
+    assert relres <= 1e-12 and info.rel_residual <= 1e-12
+    assert rel(u.ravel(), uo) < U_RTOL
+    assert abs(info.iterations - it) <= max(10, it // 50)
+    assert rel(f.ravel(), co.spmv(Ko, uo)) < 1e-7
+
+
+def test_config4_full_vs_oracle(mods, golden):
+    """BASELINE config 4 IN FULL (400x80x80, 7.9 M DOF, ~8.5 k iterations) against the oracle's full
+    Jacobi-PCG solve, recorded offline (one hour of CPU; tests/golden/oracle_config4.npz keeps a seeded
+    20,000-entry sample of u and K_full u, the norms and the iteration count)."""
+    from fea_b200 import model
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "oracle_config4.npz")
+    if not os.path.isfile(path):
+        pytest.skip("oracle_config4.npz not generated (python oracle/make_golden_large.py config4)")
+    g = golden("oracle_config4.npz")
+    C = mods["cubebeam"]
+    nodes, elements, cons, forces = C.cantilever_case(int(g["A"]), int(g["b"]))
+    u, f, info, K = model.solve_hex8(nodes, elements, cons, forces, return_info=True)
+    assert info.status == 0 and info.rel_residual <= 1e-12
+    idx = g["sample_index"]
+    umax = float(g["u_max_abs"])
+    assert np.abs(u.ravel()[idx] - g["u_sample"]).max() / umax < U_RTOL
+    assert abs(np.abs(u).max() / umax - 1.0) < U_RTOL and int(np.abs(u).argmax()) == int(g["u_argmax"])
+    assert abs(np.linalg.norm(u) / float(g["u_norm2"]) - 1.0) < U_RTOL
+    assert np.abs(f.ravel()[idx] - g["f_sample"]).max() / np.abs(g["f_sample"]).max() < 1e-6
+    assert abs(info.iterations - int(g["iterations"])) <= 100
+    ry = f[nodes[:, 2] == 0][:, 1].sum()
+    assert abs(ry - float(g["sum_reactions_y"])) < 1e-7 * abs(ry)
+
+
+def test_spmv_beyond_int32_value_offsets(mods):
+    """d*d*nnz_blocks > 2^31 (9.7 M nodes, 2.3 G matrix values, 18.6 GB): the bulk-copy SpMV computes its
+    value offsets in 64 bits.  Rigid-body translations are in the null space of the unconstrained K,
+    the product is symmetric, and the LAST rows (largest offsets) agree with an independent evaluation."""
+    core, C, U = mods["core"], mods["cubebeam"], mods["utils"]
+    if torch.cuda.mem_get_info()[0] < 60e9:
+        pytest.skip("needs ~40 GB of free device memory")
+    n2, q2 = C.generate_quad_grid(170, 170, 0.1, 0.1)
+    nd, el = U.stack_faces_2d_device(n2, q2, np.linspace(0, 1.0, 331))
+    K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX)
+    assert K.values.numel() > 2**31
+    scale = float(K.values.abs().max())
+    t = torch.zeros(K.n_dof, dtype=torch.float64, device="cuda")
+    t[1::3] = 1.0
+    assert float(K.matvec(t).abs().max()) < 1e-10 * scale
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(K.n_dof, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.randn(K.n_dof, dtype=torch.float64, device="cuda", generator=g)
+    Kx = K.matvec(x)
+    assert abs(float(Kx @ y - x @ K.matvec(y))) < 1e-9 * abs(float(Kx @ y))
+    # last 3 node rows straight from the stored blocks
+    rp = K.pattern.node_rowptr[-4:].cpu().numpy().astype(np.int64)
+    ci = K.pattern.node_colidx.cpu().numpy()
+    for i in range(3):
+        lo, hi = rp[i], rp[i + 1]
+        cnt = int(hi - lo)
+        blk = K.values[9 * lo:9 * hi].cpu().numpy().reshape(3, 3 * cnt)
+        cols = (3 * ci[lo:hi][:, None] + np.arange(3)).ravel()
+        want = blk @ x.cpu().numpy()[cols]
+        got = Kx[3 * (K.pattern.n_nodes - 3 + i):3 * (K.pattern.n_nodes - 3 + i) + 3].cpu().numpy()
+        assert np.abs(got - want).max() < 1e-9 * np.abs(want).max()
+    del K, x, y, Kx
+    torch.cuda.empty_cache()
+
+
 def test_config4_assembly_properties(mods):
     """BASELINE config 4 (400x80x80, 7.9 M DOF) assembled on one GPU: structural nnz, null space,
     SpMV linearity and symmetry <Kx, y> = <x, Ky>."""
@@ -635,12 +787,42 @@ def test_p2p_solver_single_rank(mods):
     work = torch.empty(ws, dtype=torch.uint8, device="cuda")
     res = _lib.PcgResult()
     pt = K.pattern
+    desc.algo = -1  # recurrence chosen from the size, as fea_pcg_solve does
+    _, info_h = core.pcg(K, b, history=True)
+    hist = torch.zeros(10 * n, dtype=torch.float64, device="cuda")
     for epoch in (1, 2):  # the block is reusable across solves
         desc.epoch = epoch
         rc = lib.fea_pcg_solve_p2p(pt.n_nodes, 3, pt.node_rowptr.data_ptr(), pt.node_colidx.data_ptr(),
                                    K.values.data_ptr(), pt.max_coupled, K.dinv.data_ptr(), b.data_ptr(), x.data_ptr(),
-                                   1e-12, 10 * n, work.data_ptr(), ws, ctypes.byref(desc), ctypes.byref(res), None)
+                                   1e-12, 10 * n, work.data_ptr(), ws, hist.data_ptr(), ctypes.byref(desc),
+                                   ctypes.byref(res), None)
         assert rc == 0 and res.status == 0
         assert res.iterations == info_ref.iterations
         assert torch.equal(x, u_ref)
+        # the residual history argument records what fea_pcg_solve records
+        assert np.array_equal(hist[:res.iterations].cpu().numpy(), info_h.history)
     assert lib.fea_comm_free(own.value) == 0
+
+
+def test_multi_rank_parity(tmp_path):
+    """N-rank slab solve == 1-rank solve: owned K rows bit-identical, u within 1e-10,
+    same history; peer-memory solver with both recurrences and both cut styles, the NCCL driver, and the
+    collective public cubebeam.solve.  Spawns tools/check_dist.py on 2 ranks; needs >= 2 visible GPUs
+    (`gpurun --gpus 2 -- python -m pytest tests -m gpu`)."""
+    import socket
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    out_json = tmp_path / "dist.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tools", "check_dist.py"), "48", "12", "--out",
+           str(out_json)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-4000:]
+    assert "DIST CHECK PASS" in res.stdout, res.stdout[-6000:]

