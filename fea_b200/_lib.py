@@ -108,7 +108,13 @@ PROTOTYPES = {
     "fea_pcg_multi_workspace": (c_size_t, [c_int64, c_int32]),
     "fea_pcg_solve_multi": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, c_int32, c_double, c_int32, P, c_size_t,
                                       P, ctypes.POINTER(PcgResult), P]),
-    "fea_truss_member_forces": (c_int32, [P, P, P, c_int64, P, P, P]),
+    "fea_truss_member_forces": (c_int32, [P, P, P, c_int64, c_int64, P, P, P, P, c_int32, P]),
+    "fea_truss_relax": (c_int32, [P, P, P, c_int64, c_int64, P, P, P, P, c_int64, c_double, c_int32, P, P, P, c_int32,
+                                  P]),
+    "fea_mesh_quad_grid": (c_int32, [c_int64, c_int64, c_double, c_double, P, P, P]),
+    "fea_mesh_tube_section": (c_int32, [c_int64, c_double, c_double, P, P, P]),
+    "fea_mesh_lattice_members": (c_int64, [c_int64]),
+    "fea_mesh_lattice": (c_int32, [c_int64, c_double, P, P, P, P, P, P]),
     "fea_beam_moment_shear": (c_int32, [P, P, P, c_int64, P, P, P]),
     "fea_mesh_extrude": (c_int32, [P, c_int64, P, c_int64, P, c_int64, P, P, P]),
 }

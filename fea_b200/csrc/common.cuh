@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "fea_b200.h"
 
 namespace fea {
@@ -15,12 +17,16 @@ void set_last_error(cudaError_t e);
 
 // Profiling counters (read through fea_profile_read): kernels launched by this library, and a
 // sampled CUDA-event timing of the PCG SpMV kernel taken inside fea_pcg_solve.
-struct Profile {
-  long long launches;
-  int enabled;
-  long long spmv_samples;
-  double spmv_ms;
-  long long pcg_iterations;
+struct Profile {  // every field is atomic or guarded: entry points may be called from several host threads
+  std::atomic<long long> launches{0};
+  std::atomic<int> enabled{0};
+  std::atomic<long long> spmv_samples{0};
+  std::atomic<long long> spmv_ns{0};  // sum of sampled SpMV durations, nanoseconds
+  std::atomic<long long> pcg_iterations{0};
+  void add_spmv_sample(float ms) {
+    spmv_ns += (long long)((double)ms * 1e6);
+    spmv_samples += 1;
+  }
 };
 Profile& profile();
 

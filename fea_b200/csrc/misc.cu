@@ -10,8 +10,10 @@
 
 namespace fea {
 
-static char g_err[256] = "";
-static Profile g_profile = {0, 0, 0, 0.0, 0};
+// The last CUDA error is kept per host thread (the thread that saw the failure asks for the text);
+// the profile counters are atomics.
+static thread_local char g_err[256] = "";
+static Profile g_profile;
 
 Profile& profile() { return g_profile; }
 
@@ -56,29 +58,6 @@ spmm_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int3
     const int col0 = tile * 32 * CPL + lane * CPL;
     spmm_sweep<D, CPL, G, U, false>(n_nodes, node_rowptr, node_colidx, values, X, Y, R, col0, col0 < R, lane, warp, sm,
                                     dot);
-  }
-}
-
-__global__ void truss_member_forces_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ members,
-                                           const double* __restrict__ k, int64_t n_members,
-                                           const double* __restrict__ displaced, double* __restrict__ forces) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n_members) return;
-  const int64_t a = members[2 * m], b = members[2 * m + 1];
-  double d0[3], d1[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    d0[c] = nodes[3 * b + c] - nodes[3 * a + c];
-    d1[c] = displaced[3 * b + c] - displaced[3 * a + c];
-  }
-  const double l0 = sqrt(d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2]);
-  const double l1 = sqrt(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
-  const double force = -k[m] * (l0 - l1);  // truss.py:84-88
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const double fv = force * d1[c] / l1;  // truss.py:89-90
-    atomicAdd(&forces[3 * a + c], fv);     // truss.py:91
-    atomicAdd(&forces[3 * b + c], -fv);    // truss.py:92
   }
 }
 
@@ -131,14 +110,14 @@ extern "C" void fea_profile_enable(int32_t enable) {
   g_profile.enabled = enable;
   g_profile.launches = 0;
   g_profile.spmv_samples = 0;
-  g_profile.spmv_ms = 0.0;
+  g_profile.spmv_ns = 0;
   g_profile.pcg_iterations = 0;
 }
 
 extern "C" void fea_profile_read(double* out_host) {
   out_host[0] = (double)g_profile.launches;
   out_host[1] = (double)g_profile.spmv_samples;
-  out_host[2] = g_profile.spmv_ms;
+  out_host[2] = (double)g_profile.spmv_ns.load() * 1e-6;
   out_host[3] = (double)g_profile.pcg_iterations;
 }
 
@@ -146,12 +125,8 @@ template <int D, int CPL, int G, int U, int MINB>
 static int launch_spmm_variant(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
                                const double* X, double* Y, int R, cudaStream_t stream) {
   constexpr size_t smem = sizeof(SpmmGroupSmem<D, G>) * kSpmmWarps;
-  static bool configured = false;
-  if (!configured) {
-    FEA_TRY(check(cudaFuncSetAttribute(spmm_kernel<D, CPL, G, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem)));
-    configured = true;
-  }
+  FEA_TRY(check(cudaFuncSetAttribute(spmm_kernel<D, CPL, G, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem)));  // per call: per-device attribute
   const unsigned blocks = (unsigned)std::max<int64_t>(
       1, std::min<int64_t>(ceil_div(ceil_div(n_nodes, G), kSpmmWarps), 148LL * 2 * MINB));
   spmm_kernel<D, CPL, G, U, MINB><<<blocks, 32 * kSpmmWarps, smem, stream>>>(n_nodes, rp, ci, values, X, Y, R);
@@ -180,15 +155,6 @@ extern "C" int fea_spmm(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, 
     case 3: return launch_spmm<3>(n_nodes, node_rowptr, node_colidx, values, X, Y, n_rhs, stream);
     default: return FEA_ERR_INVALID;
   }
-}
-
-extern "C" int fea_truss_member_forces(const double* nodes, const int32_t* members, const double* k,
-                                       int64_t n_members, const double* displaced, double* forces, void* stream_) {
-  if (!nodes || !members || !k || !displaced || !forces || n_members < 0) return FEA_ERR_INVALID;
-  if (n_members == 0) return FEA_OK;
-  truss_member_forces_kernel<<<(unsigned)ceil_div(n_members, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      nodes, members, k, n_members, displaced, forces);
-  return check_launch();
 }
 
 extern "C" int fea_beam_moment_shear(const double* u, const double* EI, const double* length, int64_t n_elem,

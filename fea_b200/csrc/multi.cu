@@ -387,12 +387,9 @@ template <int D, int CPL, int G, int U, int MINB>
 static int launch_multi_spmm_variant(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
                                      const double* P, double* AP, int R, const MultiWork& w, cudaStream_t stream) {
   constexpr size_t smem = sizeof(SpmmGroupSmem<D, G>) * kSpmmWarps;
-  static bool configured = false;
-  if (!configured) {
-    FEA_TRY(check(cudaFuncSetAttribute(multi_spmm_kernel<D, CPL, G, U, MINB>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-    configured = true;
-  }
+  // per call: the attribute is per device, and a process may drive several (a few hundred ns on the host)
+  FEA_TRY(check(cudaFuncSetAttribute(multi_spmm_kernel<D, CPL, G, U, MINB>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const unsigned blocks = (unsigned)std::max<int64_t>(
       1, std::min<int64_t>(ceil_div(ceil_div(n_nodes, G), kSpmmWarps), std::min(148 * 2 * MINB, kMultiBlocks)));
   multi_spmm_kernel<D, CPL, G, U, MINB><<<blocks, dim3(32, 8), smem, stream>>>(n_nodes, rp, ci, values, P, AP, R, w);

@@ -332,8 +332,7 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
       if (sample_iter[i] >= s.iter) break;  // launches after convergence are no-ops
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, sample_ev[2 * i], sample_ev[2 * i + 1]) == cudaSuccess) {
-        profile().spmv_ms += ms;
-        profile().spmv_samples += 1;
+        profile().add_spmv_sample(ms);
       }
     }
   } else if (stream != nullptr) {

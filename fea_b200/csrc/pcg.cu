@@ -190,25 +190,30 @@ pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const 
 }
 
 // step 1, bulk-copy pipeline variant (spmv_tma.cuh)
+// The gated variant is held to the ungated one's register budget (3 CTAs per SM at <3,2>): left alone
+// ptxas gives it 126 registers and one CTA per SM.
 template <int D, int G, bool GATED>
 __global__ void __launch_bounds__(tma_threads(D, G))
 pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
-                    const double* __restrict__ values, const double* __restrict__ p, double* __restrict__ ap,
-                    const double* __restrict__ p_own, int stages, int val_cap, int col_cap, PcgState* st,
+                    const double* __restrict__ values, const double* p, double* __restrict__ ap,
+                    const double* p_own, int stages, int val_cap, int col_cap, PcgState* st,
                     double* partials, const PeerView* pv) {
   extern __shared__ __align__(128) unsigned char s_tma[];
   __shared__ double s_red[32];
   if (st->done) return;
   double dot = 0.0;
-  HaloGate gate;
+  __shared__ HaloGate gate;
   if (GATED) {  // multi-GPU: interior tiles first, the halo tags are only looked at before a face tile
-    CommHeader* own = pv->hdr[pv->rank];
-    gate.tag_lower = pv->lower >= 0 ? &own->halo_tag[0] : nullptr;
-    gate.tag_upper = pv->upper >= 0 ? &own->halo_tag[1] : nullptr;
-    gate.want = peer_tag(*pv, st->iter);
-    gate.lower_tiles = pv->lower_tiles;
-    gate.upper_tiles = pv->upper_tiles;
-    gate.error = &own->error;
+    if (threadIdx.x == 0) {
+      CommHeader* own = pv->hdr[pv->rank];
+      gate.tag_lower = pv->lower >= 0 ? &own->halo_tag[0] : nullptr;
+      gate.tag_upper = pv->upper >= 0 ? &own->halo_tag[1] : nullptr;
+      gate.want = peer_tag(*pv, st->iter);
+      gate.lower_tiles = pv->lower_tiles;
+      gate.upper_tiles = pv->upper_tiles;
+      gate.error = &own->error;
+    }
+    __syncthreads();
   }
   spmv_tma_body<D, G, true, GATED>(n_nodes, node_rowptr, node_colidx, values, p, ap, p_own, stages, val_cap, col_cap,
                                    s_tma, dot, GATED ? &gate : nullptr);
@@ -1006,8 +1011,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
       if (sample_iter[i] >= s.iter) break;  // launches after convergence are no-ops: not SpMV work
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, sample_ev[2 * i], sample_ev[2 * i + 1]) == cudaSuccess) {
-        profile().spmv_ms += ms;
-        profile().spmv_samples += 1;
+        profile().add_spmv_sample(ms);
       }
     }
   } else {

@@ -46,6 +46,10 @@ constexpr int kTmaUnroll = 27;         // gathers in flight per lane and round
 __host__ __device__ constexpr int tma_items(int d) { return d * d * kTileNodes; }  // (row, b) pairs per tile
 __host__ __device__ constexpr int tma_group_warps(int d) { return (tma_items(d) + 31) / 32; }
 __host__ __device__ constexpr int tma_threads(int d, int groups) { return (groups * tma_group_warps(d) + 1) * 32; }
+// CTAs per SM the register allocation must leave room for (the pipeline wants 3 rings per SM).
+__host__ __device__ constexpr int tma_min_blocks(int d, int groups) {
+  return tma_threads(d, groups) <= 352 ? 3 : (tma_threads(d, groups) <= 512 ? 2 : 1);
+}
 __host__ __device__ constexpr size_t tma_fixed_bytes(int d, int groups) {
   return kTmaBarrierBytes + sizeof(double) * 2 * groups * tma_items(d);
 }
@@ -144,9 +148,8 @@ __device__ __forceinline__ TileRange tile_range(int r0, int r1, int total_cols) 
 // this rank's x by the neighbours' vector kernels over NVLink, followed by a tag.  Only the tiles
 // next to a slab face gather such rows, so the sweep starts `lower_tiles` tiles in (interior first;
 // the lower-face tiles wrap around to the very end) and a consumer group only looks at the tag right
-// before its first boundary tile: the halo exchange hides behind the interior of the SpMV.  Boundary
-// tiles gather x with L2-coherent loads (ld.global.cg): a 128-byte line that straddles the owned/halo
-// border may sit in L1 from an interior tile, with the halo part not yet delivered.
+// before its first boundary tile: the halo exchange hides behind the interior of the SpMV.  The gated
+// kernel gathers x with ordinary loads, not ld.global.nc (see row_part_dot).
 struct HaloGate {
   const long long* tag_lower;  // this rank's halo_tag[0] / [1]; nullptr without that neighbour
   const long long* tag_upper;
@@ -156,12 +159,30 @@ struct HaloGate {
   int* error;                  // set to 1 when a neighbour never delivers
 };
 
+// A consumer group is about to start its face tiles: its leader polls the neighbours' tags, then the
+// group's named barrier orders every thread of the group after the acquire.
+__device__ __forceinline__ void halo_gate_wait(const HaloGate* gate, bool leader, int barrier_id, int barrier_threads) {
+  if (leader) {
+    bool ok = true;
+    if (gate->tag_lower != nullptr) ok = spin_until(gate->tag_lower, gate->want, true) && ok;
+    if (gate->tag_upper != nullptr) ok = spin_until(gate->tag_upper, gate->want, true) && ok;
+    if (!ok) *gate->error = 1;
+  }
+  group_barrier(barrier_id, barrier_threads);
+}
+
 // Component b of one DOF row against x: sum_k vrow[D*k + b] * x[D*cols[k] + b].
 // `vrow` / `cols` may point to shared or global memory.  Every gather of a round is issued
 // before the first FMA.
-template <int D, bool COHERENT = false>
+// WEAK: gather with ordinary (coherent-path) global loads instead of the read-only path.  The
+// multi-GPU kernel needs it: halo rows of x are written by the neighbour GPUs while the kernel runs,
+// which ld.global.nc must never see.  Ordinary loads are covered by the memory model: they follow the
+// tag's ld.acquire.sys (+ bar.sync) in causality order, so they observe the neighbours' stores (the
+// acquire drops stale L1 lines, e.g. a 128-byte line straddling the owned / halo border that an
+// interior tile pulled in earlier); they are cached in L1 like the read-only ones.
+template <int D, bool WEAK = false>
 __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t* cols, int cnt, int b,
-                                               const double* __restrict__ x) {
+                                               const double* x) {
   double acc = 0.0;
   const double* xb = x + b;
   const double* vb = vrow + b;
@@ -170,8 +191,8 @@ __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t
 #pragma unroll
     for (int u = 0; u < kTmaUnroll; ++u) {
       const int k = k0 + u;
-      if (COHERENT)
-        xv[u] = k < cnt ? __ldcg(xb + (int64_t)D * cols[k]) : 0.0;
+      if (WEAK)
+        xv[u] = k < cnt ? xb[(int64_t)D * cols[k]] : 0.0;
       else
         xv[u] = k < cnt ? __ldg(xb + (int64_t)D * cols[k]) : 0.0;
     }
@@ -188,8 +209,8 @@ __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t
 template <int D, int G, bool DOT, bool GATED = false>
 __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __restrict__ node_rowptr,
                                               const int32_t* __restrict__ node_colidx,
-                                              const double* __restrict__ values, const double* __restrict__ x,
-                                              double* __restrict__ y, const double* __restrict__ x_own, int stages,
+                                              const double* __restrict__ values, const double* x,
+                                              double* __restrict__ y, const double* x_own, int stages,
                                               int val_cap, int col_cap, unsigned char* smem, double& dot,
                                               const HaloGate* gate = nullptr) {
   constexpr int DD = D * D;
@@ -216,7 +237,8 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
   const int total_cols = node_rowptr[n_nodes];
   const int stride = (int)gridDim.x;
   // sweep position t -> tile: rotated by the lower-face tiles when gated (interior first)
-  const int rot = GATED ? gate->lower_tiles : 0;
+  const int lower_tiles = GATED ? gate->lower_tiles : 0, upper_tiles = GATED ? gate->upper_tiles : 0;
+  const int rot = lower_tiles;
   auto tile_of = [&](int64_t t) -> int {
     const int64_t p = t + rot;
     return (int)(p < n_tiles ? p : p - n_tiles);
@@ -282,31 +304,18 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
       }
     }
     int buf_sel = 0;
-    bool seen_lower = false, seen_upper = false;
-    for (int q = group; tile64 < n_tiles; q += G) {
+    int q = group;
+    // The tile loop as a function of where it stops: the gated kernel runs it twice, over the interior
+    // positions and then over the face tiles, with the halo wait BETWEEN the two runs.  (With the wait --
+    // a spin loop and a named barrier, inlined or not -- inside the loop, ptxas took the kernel from 50 to
+    // 80 registers plus spills: 2 resident CTAs per SM instead of 3.)
+    auto sweep = [&](int64_t limit) {
+    for (; tile64 < limit; q += G) {
       const int tile = tile_of(tile64);
       const int n0 = tile * kTileNodes;
       const int n1 = n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes;
       const int node = n0 + node_in_tile;
       const bool active = has_item && node < n1;
-      bool coherent = false;
-      if (GATED) {  // group-uniform: every thread of the group works on the same tile
-        const bool need_lower = tile < gate->lower_tiles, need_upper = tile >= n_tiles - gate->upper_tiles;
-        const bool wait_lower = need_lower && !seen_lower && gate->tag_lower != nullptr;
-        const bool wait_upper = need_upper && !seen_upper && gate->tag_upper != nullptr;
-        if (wait_lower || wait_upper) {
-          if (warp == group * GW && lane == 0) {
-            bool ok = true;
-            if (wait_lower) ok = spin_until(gate->tag_lower, gate->want, true) && ok;
-            if (wait_upper) ok = spin_until(gate->tag_upper, gate->want, true) && ok;
-            if (!ok) *gate->error = 1;
-          }
-          group_barrier(1 + group, GW * 32);
-          seen_lower = seen_lower || wait_lower;
-          seen_upper = seen_upper || wait_upper;
-        }
-        coherent = need_lower || need_upper;
-      }
       tile64 += (int64_t)stride * G;
       int nr0 = 0, nr1 = 0, nlo = 0, nhi = 0;
       if (tile64 < n_tiles) {
@@ -325,8 +334,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
       if (t.direct) {
         if (active) {
           const double* vg = values + (int64_t)DD * lo + a * D * cnt;
-          part = GATED && coherent ? row_part_dot<D, true>(vg, node_colidx + lo, cnt, b, x)
-                                   : row_part_dot<D>(vg, node_colidx + lo, cnt, b, x);
+          part = row_part_dot<D, GATED>(vg, node_colidx + lo, cnt, b, x);
         }
       } else {
         const int s = q % stages;
@@ -336,8 +344,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
           const unsigned char* buf = stage0 + (size_t)s * stage_bytes;
           const double* vs = reinterpret_cast<const double*>(buf) + (int)((int64_t)DD * lo - t.v_lo);
           const int32_t* cs = reinterpret_cast<const int32_t*>(buf + sizeof(double) * val_cap) + (lo - t.c_lo);
-          part = GATED && coherent ? row_part_dot<D, true>(vs + a * D * cnt, cs, cnt, b, x)
-                                   : row_part_dot<D>(vs + a * D * cnt, cs, cnt, b, x);
+          part = row_part_dot<D, GATED>(vs + a * D * cnt, cs, cnt, b, x);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -357,6 +364,18 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
       r1 = nr1;
       lo = nlo;
       hi = nhi;
+    }
+    };
+    if (GATED) {
+      // sweep positions [0, n_tiles - lower - upper) are interior tiles, then the upper face, then the
+      // lower face (rotation above); a group that owns face tiles waits for both neighbours once
+      sweep(n_tiles - lower_tiles - upper_tiles);
+      if (tile64 < n_tiles) {  // group-uniform
+        halo_gate_wait(gate, warp == group * GW && lane == 0, 1 + group, GW * 32);
+        sweep(n_tiles);
+      }
+    } else {
+      sweep(n_tiles);
     }
   }
 }

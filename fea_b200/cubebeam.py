@@ -43,6 +43,38 @@ def generate_quad_grid(nx, ny, width, height):
     return nodes, elements
 
 
+def generate_quad_grid_device(nx, ny, width, height):
+    """`generate_quad_grid` written straight into device memory: CUDA tensors
+    (nodes (n,2) f64, elements (m,4) int32) equal to the host builder's arrays element for element."""
+    import torch
+
+    from . import _lib, core
+
+    lib = _lib.load()
+    dev = core.device()
+    nodes2d = torch.empty(((nx + 1) * (ny + 1), 2), dtype=torch.float64, device=dev)
+    quads = torch.empty((nx * ny, 4), dtype=torch.int32, device=dev)
+    _lib.check(lib.fea_mesh_quad_grid(nx, ny, float(width), float(height), nodes2d.data_ptr(), quads.data_ptr(),
+                                      core._stream()), "fea_mesh_quad_grid")
+    return nodes2d, quads
+
+
+def cantilever_case_device(A, b, width=beam_width, length=beam_length):
+    """`cantilever_case` built entirely on the device: (nodes (N,3) f64, elements (M,8) int32,
+    fixed (3N,) uint8, loads (3N,) f64) CUDA tensors, ready for core.assemble_hex8 / core.solve_system."""
+    import torch
+
+    from .utils import stack_faces_2d_device
+
+    nodes2d, quads = generate_quad_grid_device(b, b, width, width)
+    z = np.linspace(0, length, A + 1)
+    nodes, elements = stack_faces_2d_device(nodes2d, quads, z)
+    fixed = (nodes[:, 2] == 0).repeat_interleave(3).to(torch.uint8)
+    loads = torch.zeros(nodes.shape, dtype=torch.float64, device=nodes.device)
+    loads[:, 1] = (nodes[:, 1] == 0).to(torch.float64) * (linear_load * length / ((b + 1) * (A + 1)))
+    return nodes, elements, fixed, loads.reshape(-1)
+
+
 def solve(nodes, elements, constraints, forces):
     """(displacements, forces) = solve(nodes, elements, constraints, forces), cubebeam.py:79-108,
     with E = 1e7 psi and nu = 0.3 as hard-wired there (cubebeam.py:84)."""

@@ -36,6 +36,23 @@ def tube_section(n_seg=n_elements, r_in=inner_radius, r_out=outer_radius):
     return nodes2d, face2ds, forces2d
 
 
+def tube_section_device(n_seg=n_elements, r_in=inner_radius, r_out=outer_radius):
+    """Nodes and periodic quads of `tube_section` generated in device memory.
+    The connectivity equals the host builder's; the coordinates agree to the last bit or two (the
+    device's cos / sin are not numpy's)."""
+    import torch
+
+    from . import _lib, core
+
+    lib = _lib.load()
+    dev = core.device()
+    nodes2d = torch.empty((2 * n_seg, 2), dtype=torch.float64, device=dev)
+    quads = torch.empty((n_seg, 4), dtype=torch.int32, device=dev)
+    _lib.check(lib.fea_mesh_tube_section(n_seg, float(r_in), float(r_out), nodes2d.data_ptr(), quads.data_ptr(),
+                                         core._stream()), "fea_mesh_tube_section")
+    return nodes2d, quads
+
+
 def shipped_case():
     """Inputs of the reference's own run, including its load layout: fea.py:71 repeats the 2-D
     load along axis 0 although nodes are layer-major (quirk Q5) -- reproduced as is."""

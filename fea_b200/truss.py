@@ -24,45 +24,84 @@ members = [[0, 2], [1, 2]]
 loads = [[2, vec2(0.0, -100.0)]]
 
 
-def _member_forces_device(nodes_d, members_d, k_d, displaced_d):
-    lib = _lib.load()
-    out = torch.zeros_like(nodes_d)
-    _lib.check(lib.fea_truss_member_forces(nodes_d.data_ptr(), members_d.data_ptr(), k_d.data_ptr(),
-                                           members_d.shape[0], displaced_d.data_ptr(), out.data_ptr(),
-                                           core._stream()), "fea_truss_member_forces")
-    return out
+def _dtype_of(nodes, fp32):
+    """float32 when asked for, or when the caller's arrays are float32 like the script's (truss.py:9-10)."""
+    if fp32 is None:
+        fp32 = np.asarray(nodes).dtype == np.float32
+    return (np.float32, torch.float32, 1) if fp32 else (np.float64, torch.float64, 0)
 
 
-def compute_forces(nodes, members, displaced_nodes, forces, member_stiffness=None):
+def _incidence(members_d, n_nodes):
+    """node -> (member, end) incidence lists, ascending member order (the symbolic pass)."""
+    return core.symbolic(members_d, n_nodes)
+
+
+def compute_forces(nodes, members, displaced_nodes, forces, member_stiffness=None, fp32=None):
     """Accumulate the axial member forces into `forces` IN PLACE (truss.py:78-92):
     dl = |X_b - X_a| - |x_b - x_a|, F = -k dl, forces[a] += F e, forces[b] -= F e with e the
-    current member axis.  Returns None.  Evaluated in FP64 on the device and added to the
-    caller's array in its own dtype (the script's arrays are float32, truss.py:9-10).
+    current member axis.  Returns None.  Evaluated on the device node by node, every node summing its
+    members in list order (deterministic, the reference's own summation order), in the dtype of `nodes`
+    (the script's arrays are float32, truss.py:9-10) unless `fp32` says otherwise.
     `member_stiffness` (scalar or per member) defaults to the module constant `stiffness`."""
+    lib = _lib.load()
+    np_t, th_t, flag = _dtype_of(nodes, fp32)
     members_arr = np.asarray(members, dtype=np.int64).reshape(-1, 2)
-    k = np.broadcast_to(np.asarray(stiffness if member_stiffness is None else member_stiffness, dtype=np.float64),
-                        (members_arr.shape[0],))
-    nodes_d = core.to_device(np.asarray(nodes, dtype=np.float64), torch.float64)
-    disp_d = core.to_device(np.asarray(displaced_nodes, dtype=np.float64), torch.float64)
-    f = _member_forces_device(nodes_d, core.to_device(members_arr, torch.int32),
-                              core.to_device(np.ascontiguousarray(k), torch.float64), disp_d)
-    forces += f.cpu().numpy().astype(forces.dtype)
+    k = np.ascontiguousarray(np.broadcast_to(
+        np.asarray(stiffness if member_stiffness is None else member_stiffness, dtype=np_t), (members_arr.shape[0],)))
+    nodes_d = core.to_device(np.asarray(nodes, dtype=np_t), th_t)
+    disp_d = core.to_device(np.asarray(displaced_nodes, dtype=np_t), th_t)
+    members_d = core.to_device(members_arr, torch.int32)
+    k_d = core.to_device(k, th_t)
+    n = nodes_d.shape[0]
+    inc = _incidence(members_d, n)
+    out = torch.zeros_like(nodes_d)
+    _lib.check(lib.fea_truss_member_forces(nodes_d.data_ptr(), members_d.data_ptr(), k_d.data_ptr(),
+                                           members_d.shape[0], n, inc.n2e_ptr.data_ptr(), inc.n2e.data_ptr(),
+                                           disp_d.data_ptr(), out.data_ptr(), flag, core._stream()),
+               "fea_truss_member_forces")
+    forces += out.cpu().numpy().astype(forces.dtype)
 
 
-def relax(nodes, members, loads, n_steps, member_stiffness=None):
-    """`n_steps` passes of the script's loop (truss.py:97-119): member forces, residual at the
-    first loaded node (what the script prints), then x_i += (load_i + f_i) / k for loaded nodes
-    only.  Returns (displaced_nodes, residual history); dtype follows `nodes`."""
-    displaced = np.array(nodes, copy=True)
-    k = stiffness if member_stiffness is None else member_stiffness
-    history = []
-    for _ in range(n_steps):
-        forces = np.zeros_like(displaced)
-        compute_forces(nodes, members, displaced, forces, k)
-        history.append(float(np.linalg.norm(loads[0][1] + forces[loads[0][0]])))
-        for i, load in loads:
-            displaced[i] += (load + forces[i, :]) / displaced.dtype.type(stiffness)
-    return displaced, np.array(history)
+def relax(nodes, members, loads, n_steps, member_stiffness=None, fp32=None, return_residual=False):
+    """`n_steps` passes of the script's loop (truss.py:97-119) ON THE DEVICE, without a host round trip
+    per step: member forces at the loaded nodes from the current positions, residual at the first loaded
+    node (what the script prints), then x_i += (load_i + f_i) / stiffness for loaded nodes only.
+    `loads` is the script's list of [node, vector] (distinct nodes).  Returns
+    (displaced_nodes, residual history) in the dtype of `nodes` (float32 in the script)."""
+    lib = _lib.load()
+    np_t, th_t, flag = _dtype_of(nodes, fp32)
+    nodes_np = np.asarray(nodes)
+    members_arr = np.asarray(members, dtype=np.int64).reshape(-1, 2)
+    k = np.ascontiguousarray(np.broadcast_to(
+        np.asarray(stiffness if member_stiffness is None else member_stiffness, dtype=np_t), (members_arr.shape[0],)))
+    load_nodes = np.array([int(i) for i, _ in loads], dtype=np.int32)
+    if np.unique(load_nodes).size != load_nodes.size:
+        raise ValueError("loads must name distinct nodes")
+    load_vecs = np.ascontiguousarray(np.stack([np.asarray(v, dtype=np_t).reshape(3) for _, v in loads]))
+    nodes_d = core.to_device(nodes_np.astype(np_t), th_t)
+    members_d = core.to_device(members_arr, torch.int32)
+    k_d = core.to_device(k, th_t)
+    n = nodes_d.shape[0]
+    inc = _incidence(members_d, n)
+    displaced = nodes_d.clone()  # truss.py:95
+    ln_d, lv_d = core.to_device(load_nodes, torch.int32), core.to_device(load_vecs, th_t)
+    residual = torch.zeros_like(lv_d)
+    history = torch.zeros(max(n_steps, 1), dtype=torch.float64, device=nodes_d.device)
+    _lib.check(lib.fea_truss_relax(nodes_d.data_ptr(), members_d.data_ptr(), k_d.data_ptr(), members_d.shape[0], n,
+                                   inc.n2e_ptr.data_ptr(), inc.n2e.data_ptr(), ln_d.data_ptr(), lv_d.data_ptr(),
+                                   load_nodes.size, float(stiffness), int(n_steps), displaced.data_ptr(),
+                                   residual.data_ptr(), history.data_ptr(), flag, core._stream()), "fea_truss_relax")
+    out = displaced.cpu().numpy().astype(nodes_np.dtype if nodes_np.dtype.kind == "f" else np_t)
+    hist = history[:n_steps].cpu().numpy()
+    if return_residual:
+        return out, hist, residual.cpu().numpy()
+    return out, hist
+
+
+def relax_device(steps=40):
+    """The script's own case (truss.py:6-24, float32) for `steps` passes; (history, displaced)."""
+    displaced, hist = relax(nodes, members, loads, steps)
+    return hist, displaced
 
 
 def member_stiffness_matrices(nodes, members, k) -> torch.Tensor:
@@ -142,3 +181,28 @@ def lattice_truss(n: int, n_rhs: int = 64, h: float = 1.0):
     constraints[grid[:, 2] == 0] = 1
     f = np.random.default_rng(1).standard_normal((3 * n**3, n_rhs))
     return pts, mem, k, constraints, f
+
+
+def lattice_truss_device(n: int, h: float = 1.0, seed: int = 0):
+    """Nodes, members and spring rates of `lattice_truss(n)` generated directly in device memory
+    (SURVEY.md §8(f) N2): numpy's PCG64 stream of default_rng(seed) is reproduced on the device by LCG
+    jump-ahead, so the arrays equal the host generator's element for element.  Returns CUDA tensors
+    (nodes (n^3,3) f64, members (M,2) int32, k (M,) f64, constraints (n^3,3) uint8).  The load cases stay a
+    host draw: standard_normal is a rejection sampler (ziggurat), inherently sequential."""
+    import ctypes
+
+    lib = _lib.load()
+    dev = core.device()
+    st = np.random.PCG64(seed).state["state"]
+    mask = (1 << 64) - 1
+    words = (ctypes.c_uint64 * 4)(st["state"] >> 64, st["state"] & mask, st["inc"] >> 64, st["inc"] & mask)
+    m = int(lib.fea_mesh_lattice_members(n))
+    pts = torch.empty((n**3, 3), dtype=torch.float64, device=dev)
+    mem = torch.empty((m, 2), dtype=torch.int32, device=dev)
+    k = torch.empty(m, dtype=torch.float64, device=dev)
+    scratch = torch.empty(14, dtype=torch.int64, device=dev)
+    _lib.check(lib.fea_mesh_lattice(n, float(h), ctypes.addressof(words), pts.data_ptr(), mem.data_ptr(), k.data_ptr(),
+                                    scratch.data_ptr(), core._stream()), "fea_mesh_lattice")
+    constraints = torch.zeros((n**3, 3), dtype=torch.uint8, device=dev)
+    constraints[: n * n] = 1  # iz = 0: the first n^2 node ids
+    return pts, mem, k, constraints

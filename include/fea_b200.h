@@ -306,9 +306,29 @@ int fea_pcg_solve_multi(int64_t n_nodes, int32_t dof_per_node, const int32_t* no
  * ---------------------------------------------------------------------------------------- */
 
 /* compute_forces(nodes, members, displaced_nodes, forces), truss.py:78-92: accumulates member
- * forces into `forces` (n_nodes,3) IN PLACE.  k: per-member spring rate. FP64. */
-int fea_truss_member_forces(const double* nodes, const int32_t* members, const double* k,
-                            int64_t n_members, const double* displaced, double* forces, void* stream);
+ * forces into `forces` (n_nodes,3) IN PLACE.  k: per-member spring rate.  Node-parallel over the
+ * node -> member incidence lists of the symbolic pass (n2m_ptr / n2m = n2e_ptr / n2e of
+ * fea_csr_symbolic_count on the (n_members, 2) connectivity): every node adds its members'
+ * contributions in ascending member order, the order of the reference's loop -- deterministic,
+ * no floating-point atomics.  fp32 != 0: nodes / k / displaced / forces are float (the script's own
+ * dtype, truss.py:9-10), else double. */
+int fea_truss_member_forces(const void* nodes, const int32_t* members, const void* k,
+                            int64_t n_members, int64_t n_nodes, const int32_t* n2m_ptr,
+                            const int32_t* n2m, const void* displaced, void* forces, int32_t fp32,
+                            void* stream);
+
+/* The relaxation loop of truss.py:95-119, n_steps passes, entirely on the device (two small kernels
+ * per step, no host round trip): forces from the current positions, residual_i = load_i + f_i for the
+ * n_loads loaded nodes (distinct), history[step] = |residual of the FIRST load| (what the script
+ * prints, truss.py:101-103), then displaced_i += residual_i / stiffness for loaded nodes only.
+ * load_nodes int32 [n_loads], load_vecs [n_loads,3], displaced [n_nodes,3] in/out (start: a copy of
+ * nodes, truss.py:95), residual [n_loads,3] scratch/out (the last step's residuals), history double
+ * [n_steps] (may be NULL).  fp32 as above. */
+int fea_truss_relax(const void* nodes, const int32_t* members, const void* k, int64_t n_members,
+                    int64_t n_nodes, const int32_t* n2m_ptr, const int32_t* n2m,
+                    const int32_t* load_nodes, const void* load_vecs, int64_t n_loads,
+                    double stiffness, int32_t n_steps, void* displaced, void* residual,
+                    double* history, int32_t fp32, void* stream);
 
 /* moment_vector / shear_vector of euler_bernoulli.py:76-102 (the reference's own formulas). */
 int fea_beam_moment_shear(const double* u, const double* EI, const double* length, int64_t n_elem,
@@ -319,6 +339,27 @@ int fea_beam_moment_shear(const double* u, const double* EI, const double* lengt
 int fea_mesh_extrude(const double* nodes2d, int64_t n2d, const int32_t* faces2d, int64_t n_faces,
                      const double* z_heights, int64_t n_layers, double* nodes3d, int32_t* elements,
                      void* stream);
+
+/* generate_quad_grid(nx, ny, width, height), cubebeam.py:28-57, in device memory: nodes2d
+ * [(nx+1)(ny+1), 2] x-fastest with np.linspace's values, quads int32 [nx*ny, 4] = [n1, n2, n4, n3]. */
+int fea_mesh_quad_grid(int64_t nx, int64_t ny, double width, double height, double* nodes2d,
+                       int32_t* quads, void* stream);
+
+/* Tube cross-section of fea.py:28-48: nodes2d [2*n_seg, 2] (inner ring, then outer ring, angles
+ * i * 2 pi / n_seg), periodic quads int32 [n_seg, 4] = [i, i+n, (i+1)%n + n, (i+1)%n]. */
+int fea_mesh_tube_section(int64_t n_seg, double r_in, double r_out, double* nodes2d, int32_t* quads,
+                          void* stream);
+
+/* BASELINE config 5's frozen generator: jittered cubic lattice of n^3 nodes, members
+ * along the 13 half-space neighbour directions (fea_mesh_lattice_members(n) of them, direction by
+ * direction, start nodes in id order), per-member spring rates.  The random draws are numpy's PCG64
+ * stream: pcg64_state_host[4] = {state hi, state lo, inc hi, inc lo} of np.random.PCG64(seed)
+ * (default_rng(0) for the frozen case); nodes = grid*h + uniform(-0.1h, 0.1h) consumes draws
+ * [0, 3n^3), k = uniform(500, 1500) the next M, each thread jumping ahead to its chunk (LCG
+ * skip-ahead).  nodes [n^3,3], members int32 [M,2], k [M], dir_offset_dev int64 [14] scratch. */
+int64_t fea_mesh_lattice_members(int64_t n);
+int fea_mesh_lattice(int64_t n, double h, const uint64_t* pcg64_state_host, double* nodes,
+                     int32_t* members, double* k, int64_t* dir_offset_dev, void* stream);
 
 #ifdef __cplusplus
 }

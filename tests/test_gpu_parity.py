@@ -400,12 +400,80 @@ def test_k8_truss(mods, golden):
     f += 1.0  # accumulates in place
     T.compute_forces(n64, g["members"], g["probe"], f)
     assert rel(f, 2 * g["f_probe"] + 1.0) < 1e-13
+    # the script's loop for 40 passes, on the device, in the script's own float32 (truss.py:9-10)
     disp, hist = T.relax(T.nodes, T.members, T.loads, 40)
     assert disp.dtype == np.float32
-    assert np.allclose(hist, g["residual_history"], rtol=2e-3, atol=2e-4)  # float32 script vs FP64 kernel
-    assert np.allclose(disp, g["displaced_history"][-1], atol=1e-5)
+    assert np.allclose(hist, g["residual_history"], rtol=2e-5, atol=2e-5)
+    assert np.allclose(disp, g["displaced_history"][-1], atol=2e-6)
+    # ... and in FP64 against the oracle's FP64 relaxation
+    d64, h64 = T.relax(n64, g["members"], [[int(g["load_node"]), g["load"].astype(np.float64)]], 40)
+    od = n64.copy()
+    oh = [fo.truss_relax_step(n64, g["members"], od, [[int(g["load_node"]), g["load"].astype(np.float64)]],
+                              float(g["stiffness"])) for _ in range(40)]
+    assert d64.dtype == np.float64 and np.allclose(h64, oh, rtol=1e-12, atol=1e-12) and rel(d64, od) < 1e-13
     u, K, info = T.solve_linear(*T.shipped_case(), return_matrix=True)
     assert np.allclose(u[2], [0.0, -0.25, 0.0], atol=1e-14)
+
+
+def test_truss_relax_device_lattice(mods):
+    """The relaxation loop on a lattice with many loaded nodes (one in five), per-member spring rates:
+    25 passes on the device against the oracle's loop; the member-force evaluation is deterministic
+    (node-owner gather in member order, no atomics): two runs are bit-identical."""
+    T = mods["truss"]
+    nodes, members, k, cons, _ = T.lattice_truss(7, n_rhs=1)
+    rng = np.random.default_rng(5)
+    loaded = np.sort(rng.choice(np.arange(49, nodes.shape[0]), nodes.shape[0] // 5, replace=False))
+    loads = [[int(i), 20.0 * rng.standard_normal(3)] for i in loaded]
+    d1, h1, r1 = T.relax(nodes, members, loads, 25, member_stiffness=k, return_residual=True)
+    d2, h2, r2 = T.relax(nodes, members, loads, 25, member_stiffness=k, return_residual=True)
+    assert np.array_equal(d1, d2) and np.array_equal(h1, h2) and np.array_equal(r1, r2)
+    # the oracle's loop with per-member k in the forces and the module constant in the update
+    od = nodes.copy()
+    oh = []
+    for _ in range(25):
+        f = np.zeros_like(nodes)
+        fo.truss_compute_forces(nodes, members, od, f, k)
+        oh.append(float(np.linalg.norm(loads[0][1] + f[loads[0][0]])))
+        for i, load in loads:
+            od[i] += (load + f[i]) / T.stiffness
+    assert np.allclose(h1, oh, rtol=1e-11) and rel(d1, od) < 1e-12
+    f = np.zeros_like(nodes)
+    T.compute_forces(nodes, members, d1, f, member_stiffness=k)
+    fo_ = np.zeros_like(nodes)
+    fo.truss_compute_forces(nodes, members, od, fo_, k)
+    assert rel(f, fo_) < 1e-9
+    with pytest.raises(ValueError):
+        T.relax(nodes, members, [loads[0], loads[0]], 2)
+
+
+def test_device_mesh_builders(mods):
+    """the input generators on the device equal the host builders element for element
+    (quad grid incl. np.linspace's rounding, extrusion, tube connectivity, config-5 lattice incl. numpy's
+    PCG64 stream); tube coordinates agree to the last bit or two (device cos / sin)."""
+    C, F, T, U, core = mods["cubebeam"], mods["fea"], mods["truss"], mods["utils"], mods["core"]
+    for nx, ny, w, h in ((4, 4, 0.1, 0.1), (7, 3, 0.3, 0.2), (80, 80, 0.1, 0.1), (1, 1, 1.0, 2.0), (33, 129, 0.7, 1.3)):
+        n2, q2 = C.generate_quad_grid(nx, ny, w, h)
+        dn, dq = C.generate_quad_grid_device(nx, ny, w, h)
+        assert np.array_equal(dn.cpu().numpy(), n2) and np.array_equal(dq.cpu().numpy(), q2)
+    nodes, elements, cons, forces = C.cantilever_case(37, 9)
+    dn, de, dfix, dload = C.cantilever_case_device(37, 9)
+    assert np.array_equal(dn.cpu().numpy(), nodes) and np.array_equal(de.cpu().numpy(), elements)
+    assert np.array_equal(dfix.cpu().numpy(), (cons.ravel() != 0).astype(np.uint8))
+    assert np.array_equal(dload.cpu().numpy(), forces.ravel())
+    for n_seg in (26, 7, 360):
+        n2, q2, _ = F.tube_section(n_seg)
+        dn, dq = F.tube_section_device(n_seg)
+        assert np.array_equal(dq.cpu().numpy(), q2)
+        assert np.abs(dn.cpu().numpy() - n2).max() <= 4e-16 * F.outer_radius
+    for n in (2, 5, 12):
+        pts, mem, k, cons, _ = T.lattice_truss(n, n_rhs=1)
+        dp, dm, dk, dc = T.lattice_truss_device(n)
+        assert dm.shape[0] == 3 * n * n * (n - 1) + 6 * n * (n - 1) ** 2 + 4 * (n - 1) ** 3
+        assert np.array_equal(dp.cpu().numpy(), pts) and np.array_equal(dm.cpu().numpy(), mem)
+        assert np.array_equal(dk.cpu().numpy(), k) and np.array_equal(dc.cpu().numpy() != 0, cons != 0)
+    pts, mem, k, cons, _ = T.lattice_truss(9, n_rhs=1, h=0.37)
+    dp, dm, dk, dc = T.lattice_truss_device(9, h=0.37)
+    assert np.array_equal(dp.cpu().numpy(), pts) and np.array_equal(dk.cpu().numpy(), k)
 
 
 def test_truss_lattice_multi_rhs(mods):
