@@ -105,6 +105,8 @@ PROTOTYPES = {
     "fea_comm_ipc_close": (c_int32, [P]),
     "fea_pcg_solve_p2p": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, P, c_double, c_int32, P, c_size_t, P,
                                     ctypes.POINTER(PeerComm), ctypes.POINTER(PcgResult), P]),
+    "fea_chain_solve_workspace": (c_size_t, [c_int64, c_int32, c_int32]),
+    "fea_chain_solve": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, c_int32, P, c_size_t, P, P]),
     "fea_pcg_multi_workspace": (c_size_t, [c_int64, c_int32]),
     "fea_pcg_solve_multi": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, c_int32, c_double, c_int32, P, c_size_t,
                                       P, ctypes.POINTER(PcgResult), P]),
@@ -174,6 +176,8 @@ def raise_for_status(status_host: np.ndarray) -> None:
         err = ValueError("zero-length truss member")
         err.element = index
         raise err
+    if code == FEA_ERR_INVALID:
+        raise ValueError(f"mesh is not a chain at node {index}")
     if code == FEA_ERR_BREAKDOWN:
         raise np.linalg.LinAlgError("Singular matrix")  # what np.linalg.solve raises, cubebeam.py:98
     if code == FEA_ERR_MAXITER:

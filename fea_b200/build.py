@@ -19,7 +19,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(CSRC, "libfea_b200.so")
-SOURCES = ["symbolic.cu", "element_ke.cu", "assemble.cu", "pcg.cu", "p2p.cu", "multi.cu", "misc.cu", "host.cu", "mesh.cu", "truss.cu"]
+SOURCES = ["symbolic.cu", "element_ke.cu", "assemble.cu", "pcg.cu", "p2p.cu", "multi.cu", "misc.cu", "host.cu", "mesh.cu", "truss.cu", "chain.cu"]
 HEADERS = ["common.cuh", "hex8.cuh", "spmv.cuh"]
 
 NVCC_FLAGS = [

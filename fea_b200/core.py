@@ -269,6 +269,36 @@ def pcg(A: BlockCSR, b: torch.Tensor, tol: float = 1e-12, max_iter: int | None =
     return x, info
 
 
+def chain_solve(A: BlockCSR, b: torch.Tensor, extended: bool = True):
+    """Direct solve of a chain mesh (block-tridiagonal K, 1 or 2 DOF per node) by parallel cyclic
+    reduction; constrained DOF (A.fixed) come back exactly 0.  Replaces np.linalg.solve of
+    euler_bernoulli.py:69.  `extended`: eliminate in double-double arithmetic (default; the beam's
+    cond(K) ~ 5 n^4 leaves FP64 elimination nothing beyond n of a few thousand).  ValueError if the
+    pattern is not a chain, LinAlgError for a singular pivot."""
+    lib = _lib.load()
+    pt = A.pattern
+    n = pt.n_nodes
+    b = b.contiguous()
+    x = torch.empty(A.n_dof, dtype=torch.float64, device=b.device)
+    ext = 1 if extended else 0
+    ws_bytes = lib.fea_chain_solve_workspace(n, A.dof_per_node, ext)
+    work = torch.empty(ws_bytes, dtype=torch.uint8, device=b.device)
+    status = _status_slot()
+    _lib.check(lib.fea_chain_solve(n, A.dof_per_node, _p(pt.node_rowptr), _p(pt.node_colidx), _p(A.values),
+                                   _p(A.fixed), _p(b), _p(x), ext, _p(work), ws_bytes, _p(status), _stream()),
+               "fea_chain_solve")
+    _check_status(status)
+    free = A.dinv != 0 if A.dinv is not None else None
+    r = b - A.matvec(x)
+    if free is not None:
+        r = r[free]
+        bn = b[free].norm()
+    else:
+        bn = b.norm()
+    rel = float(r.norm() / bn) if float(bn) > 0 else 0.0
+    return x, SolveInfo(0, rel, float(bn), _lib.FEA_OK, None)
+
+
 def pcg_multi(A: BlockCSR, B: torch.Tensor, tol: float = 1e-12, max_iter: int | None = None,
               raise_on_failure: bool = True):
     """Batched multi-RHS Jacobi-PCG (BASELINE config 5): B, X are (n_dof, n_rhs) row-major."""

@@ -66,7 +66,10 @@ __global__ void __launch_bounds__(32) p2p_init_exchange_kernel(PeerView pv, PcgS
   }
   if (lane == 0) {
     if (!ok) {
-      peer_failure(pv, st);
+      pv.hdr[pv.rank]->error = 1;
+      st->status = FEA_ERR_PEER;
+      st->done = 1;
+      st->rr_final = st->rr;
     } else {
       st->rz = s0;
       st->bnorm2 = s1;
@@ -184,6 +187,14 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   }
   if (pv.lower < 0) pv.lower_tiles = 0;
   if (pv.upper < 0) pv.upper_tiles = 0;
+  // experiment switches: FEA_HALO_GATE=0 waits for the halo before the FIRST tile (no
+  // overlap, the round-1 behaviour moved into the SpMV); FEA_P2P_FORCE_GATED=1 runs the gated kernels on
+  // a single rank too (A/B of the gated against the plain SpMV on one GPU)
+  if (const char* env = std::getenv("FEA_HALO_GATE")) {
+    if (env[0] == '0') pv.lower_tiles = pv.upper_tiles = (int)n_tiles;
+  }
+  const char* force_env = std::getenv("FEA_P2P_FORCE_GATED");
+  const bool force_gated = force_env != nullptr && force_env[0] == '1';
   for (int i = 0; i < comm->world; ++i) {
     if (!comm->comm[i]) return FEA_ERR_INVALID;
     pv.hdr[i] = static_cast<CommHeader*>(comm->comm[i]);
@@ -230,7 +241,18 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   auto halo = [&]() {
     if (multi) p2p_halo_kernel<<<halo_blocks, 256, 0, stream>>>(pv, state);
   };
-  const PeerView* pv_it = multi ? pv_dev : nullptr;
+  PeerLaunch peer;
+  peer.view = pv_dev;
+  peer.key.own = pv.hdr[pv.rank];
+  peer.key.epoch = pv.epoch;
+  peer.key.world = pv.world;
+  peer.key.rank = pv.rank;
+  peer.key.lower_tiles = pv.lower_tiles;
+  peer.key.upper_tiles = pv.upper_tiles;
+  peer.key.has_lower = pv.lower >= 0;
+  peer.key.has_upper = pv.upper >= 0;
+  const PeerLaunch* peer_it = multi || force_gated ? &peer : nullptr;
+  const PeerView* pv_it = peer_it ? pv_dev : nullptr;
   // measurement hook (as in fea_pcg_solve): CUDA-event pairs around one SpMV launch per chunk
   constexpr int kMaxSamples = 256;
   cudaEvent_t* sample_ev = nullptr;
@@ -245,14 +267,14 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     if (sample) sample_iter[n_samples] = (int)enqueued;
     if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
     const int r1 = pcg_step_spmv(d, n_owned_nodes, node_rowptr_owned, node_colidx, values, p_ext, ap,
-                                 comm->own_offset_nodes, state, partials, stream, &plan, pv_it);
+                                 comm->own_offset_nodes, state, partials, stream, &plan, peer_it);
     if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
     if (algo == 1) {  // p_own holds u = dinv r here (the SpMV input)
       pcg_cgcg_kernel<<<cgcg_blocks(n), 256, 0, stream>>>(n, dinv, p_own, ap, p2, s_vec, x, r, state, partials, history,
-                                                          pv_it);
+                                                          pv_it, peer.key);
     } else {
-      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials, pv_it);
-      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, history, pv_it);
+      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials, pv_it, peer.key);
+      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, history, pv_it, peer.key);
     }
     return r1;
   };

@@ -111,7 +111,8 @@ __device__ __forceinline__ double reduce_partials(const double* partials, double
 }
 
 // Last block of a PCG SpMV: p.Ap of this rank -> state; with peers, warp 0 also publishes it.
-__device__ __forceinline__ void finish_pap(const double* partials, double* s_red, PcgState* st, const PeerView* pv) {
+__device__ __forceinline__ void finish_pap(const double* partials, double* s_red, PcgState* st, const PeerView* pv,
+                                           const PeerKey& key) {
   const double s = reduce_partials(partials, s_red);
   if (threadIdx.x == 0) {
     st->pap = s;
@@ -120,18 +121,17 @@ __device__ __forceinline__ void finish_pap(const double* partials, double* s_red
   }
   if (pv != nullptr) {
     __syncthreads();
-    if (threadIdx.x == 0 && pv->hdr[pv->rank]->error != 0) peer_failure(*pv, st);  // a halo gate timed out
+    if (threadIdx.x == 0 && key.own->error != 0) peer_failure(key, st);  // a halo gate timed out
     if (threadIdx.x < 32) peer_publish(*pv, 1, st->iter, s_red[0], 0.0);
   }
 }
 
 // Multi-GPU: hold the calling thread until the neighbours' halo rows of this iteration have landed.
-__device__ __forceinline__ bool wait_halo(const PeerView& pv, long long iter) {
-  const long long tag = peer_tag(pv, iter);
-  CommHeader* own = pv.hdr[pv.rank];
+__device__ __forceinline__ bool wait_halo(const PeerKey& key, long long iter) {
+  const long long tag = peer_tag(key, iter);
   bool ok = true;
-  if (pv.lower >= 0) ok = spin_until(&own->halo_tag[0], tag, true) && ok;
-  if (pv.upper >= 0) ok = spin_until(&own->halo_tag[1], tag, true) && ok;
+  if (key.has_lower) ok = spin_until(&key.own->halo_tag[0], tag, true) && ok;
+  if (key.has_upper) ok = spin_until(&key.own->halo_tag[1], tag, true) && ok;
   return ok;
 }
 
@@ -161,11 +161,11 @@ template <int D>
 __global__ void __launch_bounds__(kSpmvThreads)
 pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                 const double* __restrict__ values, const double* __restrict__ p, double* __restrict__ ap,
-                int64_t p_row_offset, PcgState* st, double* partials, const PeerView* pv) {
+                int64_t p_row_offset, PcgState* st, double* partials, const PeerView* pv, PeerKey key) {
   __shared__ double s_red[32];
   if (st->done) return;
   if (pv != nullptr) {  // no tile ordering here: every block waits for the halo before its first gather
-    if (threadIdx.x == 0 && !wait_halo(*pv, st->iter)) pv->hdr[pv->rank]->error = 1;
+    if (threadIdx.x == 0 && !wait_halo(key, st->iter)) key.own->error = 1;
     __syncthreads();
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -186,7 +186,7 @@ pcg_spmv_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const 
     }
   }
   const double total = block_sum(dot, s_red);
-  if (publish_partials(partials, 1, &total, &st->counter[0])) finish_pap(partials, s_red, st, pv);
+  if (publish_partials(partials, 1, &total, &st->counter[0])) finish_pap(partials, s_red, st, pv, key);
 }
 
 // step 1, bulk-copy pipeline variant (spmv_tma.cuh)
@@ -197,28 +197,25 @@ __global__ void __launch_bounds__(tma_threads(D, G))
 pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                     const double* __restrict__ values, const double* p, double* __restrict__ ap,
                     const double* p_own, int stages, int val_cap, int col_cap, PcgState* st,
-                    double* partials, const PeerView* pv) {
+                    double* partials, const PeerView* pv, PeerKey key) {
   extern __shared__ __align__(128) unsigned char s_tma[];
   __shared__ double s_red[32];
   if (st->done) return;
   double dot = 0.0;
-  __shared__ HaloGate gate;
+  HaloGate gate{};
   if (GATED) {  // multi-GPU: interior tiles first, the halo tags are only looked at before a face tile
-    if (threadIdx.x == 0) {
-      CommHeader* own = pv->hdr[pv->rank];
-      gate.tag_lower = pv->lower >= 0 ? &own->halo_tag[0] : nullptr;
-      gate.tag_upper = pv->upper >= 0 ? &own->halo_tag[1] : nullptr;
-      gate.want = peer_tag(*pv, st->iter);
-      gate.lower_tiles = pv->lower_tiles;
-      gate.upper_tiles = pv->upper_tiles;
-      gate.error = &own->error;
-    }
-    __syncthreads();
+    gate.tag_lower = key.has_lower ? &key.own->halo_tag[0] : nullptr;
+    gate.tag_upper = key.has_upper ? &key.own->halo_tag[1] : nullptr;
+    gate.iter = &st->iter;
+    gate.epoch = key.epoch;
+    gate.lower_tiles = key.lower_tiles;
+    gate.upper_tiles = key.upper_tiles;
+    gate.error = &key.own->error;
   }
   spmv_tma_body<D, G, true, GATED>(n_nodes, node_rowptr, node_colidx, values, p, ap, p_own, stages, val_cap, col_cap,
-                                   s_tma, dot, GATED ? &gate : nullptr);
+                                   s_tma, dot, gate);
   const double total = block_sum(dot, s_red);
-  if (publish_partials(partials, 1, &total, &st->counter[0])) finish_pap(partials, s_red, st, pv);
+  if (publish_partials(partials, 1, &total, &st->counter[0])) finish_pap(partials, s_red, st, pv, key);
 }
 
 // Launch configuration of one kernel instance, cached per device.
@@ -256,20 +253,20 @@ static int tma_grid(GridCache& cache, Kernel kernel, const TmaPlan& plan, int th
 template <int D, int G>
 static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
                       const double* values, const double* x, double* y, int64_t off, PcgState* st, double* partials,
-                      cudaStream_t stream, const PeerView* pv) {
+                      cudaStream_t stream, const PeerLaunch* peer) {
   const TmaLayout& L = plan.layout;
   const int n = (int)n_nodes;
   int grid = 0;
-  if (dot && pv != nullptr) {
+  if (dot && peer != nullptr) {
     static GridCache cache;
     FEA_TRY(tma_grid(cache, pcg_spmv_tma_kernel<D, G, true>, plan, tma_threads(D, G), &grid));
     pcg_spmv_tma_kernel<D, G, true><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(
-        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, pv);
+        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, peer->view, peer->key);
   } else if (dot) {
     static GridCache cache;
     FEA_TRY(tma_grid(cache, pcg_spmv_tma_kernel<D, G, false>, plan, tma_threads(D, G), &grid));
     pcg_spmv_tma_kernel<D, G, false><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(
-        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, nullptr);
+        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, nullptr, PeerKey{});
   } else {
     static GridCache cache;
     FEA_TRY(tma_grid(cache, spmv_tma_kernel<D, G>, plan, tma_threads(D, G), &grid));
@@ -282,23 +279,23 @@ static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int3
 template <int D>
 static int launch_tma_g(const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
                         const double* values, const double* x, double* y, int64_t off, PcgState* st,
-                        double* partials, cudaStream_t stream, const PeerView* pv) {
+                        double* partials, cudaStream_t stream, const PeerLaunch* peer) {
   switch (plan.groups) {
-    case 1: return launch_tma<D, 1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
-    case 2: return launch_tma<D, 2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
-    case 3: return launch_tma<D, 3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
-    case 4: return launch_tma<D, 4>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
+    case 1: return launch_tma<D, 1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, peer);
+    case 2: return launch_tma<D, 2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, peer);
+    case 3: return launch_tma<D, 3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, peer);
+    case 4: return launch_tma<D, 4>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, peer);
     default: return FEA_ERR_INVALID;
   }
 }
 
 static int dispatch_tma(int d, const TmaPlan& plan, bool dot, int64_t n_nodes, const int32_t* rp, const int32_t* ci,
                         const double* values, const double* x, double* y, int64_t off, PcgState* st,
-                        double* partials, cudaStream_t stream, const PeerView* pv = nullptr) {
+                        double* partials, cudaStream_t stream, const PeerLaunch* peer = nullptr) {
   switch (d) {
-    case 1: return launch_tma_g<1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
-    case 2: return launch_tma_g<2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
-    case 3: return launch_tma_g<3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, pv);
+    case 1: return launch_tma_g<1>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, peer);
+    case 2: return launch_tma_g<2>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, peer);
+    case 3: return launch_tma_g<3>(plan, dot, n_nodes, rp, ci, values, x, y, off, st, partials, stream, peer);
     default: return FEA_ERR_INVALID;
   }
 }
@@ -332,7 +329,7 @@ __device__ __forceinline__ bool stagnated(PcgState* st, double rr, int iter) {
 __global__ void __launch_bounds__(256)
 pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ p,
                   const double* __restrict__ ap, double* __restrict__ x, double* __restrict__ r, PcgState* st,
-                  double* partials, const PeerView* pv) {
+                  double* partials, const PeerView* pv, PeerKey key) {
   __shared__ double s_red[32];
   __shared__ double s_glob[2];
   __shared__ int s_ok;
@@ -343,7 +340,7 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
   if (pv != nullptr) {  // p.Ap of all ranks: every CTA forms the same rank-ordered sum
     if (threadIdx.x < 32) {
       double a, b;
-      const bool ok = peer_collect(*pv, 1, iter, a, b);
+      const bool ok = peer_collect(key, 1, iter, a, b);
       if (threadIdx.x == 0) {
         s_glob[0] = a;
         s_ok = ok;
@@ -351,7 +348,7 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
     }
     __syncthreads();
     if (!s_ok) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(*pv, st);
+      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(key, st);
       return;
     }
     pap = s_glob[0];
@@ -427,7 +424,7 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
 // step 3
 __global__ void __launch_bounds__(256)
 pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
-                     double* __restrict__ p, PcgState* st, double* history, const PeerView* pv) {
+                     double* __restrict__ p, PcgState* st, double* history, const PeerView* pv, PeerKey key) {
   __shared__ bool s_last;
   __shared__ double s_glob[2];
   __shared__ int s_ok;
@@ -438,7 +435,7 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
   if (pv != nullptr) {  // r.z and r.r of all ranks
     if (threadIdx.x < 32) {
       double a, b;
-      const bool ok = peer_collect(*pv, 2, iter - 1, a, b);
+      const bool ok = peer_collect(key, 2, iter - 1, a, b);
       if (threadIdx.x == 0) {
         s_glob[0] = a;
         s_glob[1] = b;
@@ -447,7 +444,7 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
     }
     __syncthreads();
     if (!s_ok) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(*pv, st);
+      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(key, st);
       return;
     }
     rz_new = s_glob[0];
@@ -544,7 +541,7 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
 __global__ void __launch_bounds__(256, 3)
 pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__ u, const double* __restrict__ w,
                 double* __restrict__ p, double* __restrict__ s, double* __restrict__ x, double* __restrict__ r,
-                PcgState* st, double* partials, double* history, const PeerView* pv) {
+                PcgState* st, double* partials, double* history, const PeerView* pv, PeerKey key) {
   __shared__ double s_red[32];
   __shared__ double s_glob[3];
   __shared__ int s_ok;
@@ -555,7 +552,7 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
   if (pv != nullptr) {  // world sums: u.w of this iteration, (r.u, r.r) of the previous one
     if (threadIdx.x < 32) {
       double a, c, d;
-      const bool ok = peer_collect2(*pv, 1, iter, 2, (long long)iter - 1, a, c, d);
+      const bool ok = peer_collect2(key, 1, iter, 2, (long long)iter - 1, a, c, d);
       if (threadIdx.x == 0) {
         s_glob[0] = a;
         s_glob[1] = c;
@@ -565,7 +562,7 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
     }
     __syncthreads();
     if (!s_ok) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(*pv, st);
+      if (blockIdx.x == 0 && threadIdx.x == 0) peer_failure(key, st);
       return;
     }
     delta = s_glob[0];
@@ -766,21 +763,21 @@ int pcg_algorithm(int64_t n_dof, bool multi_gpu) {  // read per solve, so that a
 template <int D>
 static int launch_step_spmv(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
                             const double* p, double* ap, int64_t off, PcgState* st, double* partials,
-                            cudaStream_t stream, const PeerView* pv) {
-  pcg_spmv_kernel<D><<<spmv_blocks(n_nodes), kSpmvThreads, 0, stream>>>(n_nodes, rp, ci, values, p, ap, off, st,
-                                                                        partials, pv);
+                            cudaStream_t stream, const PeerLaunch* peer) {
+  pcg_spmv_kernel<D><<<spmv_blocks(n_nodes), kSpmvThreads, 0, stream>>>(
+      n_nodes, rp, ci, values, p, ap, off, st, partials, peer ? peer->view : nullptr, peer ? peer->key : PeerKey{});
   return FEA_OK;
 }
 
 int pcg_step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
                   const double* p, double* ap, int64_t off, PcgState* st, double* partials, cudaStream_t stream,
-                  const TmaPlan* plan, const PeerView* pv) {
+                  const TmaPlan* plan, const PeerLaunch* peer) {
   if (plan != nullptr && plan->ok)
-    return dispatch_tma(d, *plan, true, n_nodes, rp, ci, values, p, ap, off, st, partials, stream, pv);
+    return dispatch_tma(d, *plan, true, n_nodes, rp, ci, values, p, ap, off, st, partials, stream, peer);
   switch (d) {
-    case 1: return launch_step_spmv<1>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, pv);
-    case 2: return launch_step_spmv<2>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, pv);
-    case 3: return launch_step_spmv<3>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, pv);
+    case 1: return launch_step_spmv<1>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, peer);
+    case 2: return launch_step_spmv<2>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, peer);
+    case 3: return launch_step_spmv<3>(n_nodes, rp, ci, values, p, ap, off, st, partials, stream, peer);
     default: return FEA_ERR_INVALID;
   }
 }
@@ -861,7 +858,7 @@ extern "C" int fea_pcg_step_update(int64_t n_dof, const double* dinv, const doub
                                    double* r, void* state, void* partials, void* stream_) {
   if (!dinv || !p || !ap || !x || !r || !state || !partials || n_dof <= 0) return FEA_ERR_INVALID;
   pcg_update_kernel<<<vec_blocks(n_dof), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      n_dof, dinv, p, ap, x, r, static_cast<PcgState*>(state), static_cast<double*>(partials), nullptr);
+      n_dof, dinv, p, ap, x, r, static_cast<PcgState*>(state), static_cast<double*>(partials), nullptr, PeerKey{});
   return check_launch();
 }
 
@@ -869,7 +866,7 @@ extern "C" int fea_pcg_step_direction(int64_t n_dof, const double* dinv, const d
                                       double* history, void* stream_) {
   if (!dinv || !r || !p || !state || n_dof <= 0) return FEA_ERR_INVALID;
   pcg_direction_kernel<<<vec_blocks(n_dof), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      n_dof, dinv, r, p, static_cast<PcgState*>(state), history, nullptr);
+      n_dof, dinv, r, p, static_cast<PcgState*>(state), history, nullptr, PeerKey{});
   return check_launch();
 }
 
@@ -940,10 +937,10 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
     if (algo == 1) {
       pcg_cgcg_kernel<<<cgcg_blocks(n), 256, 0, stream>>>(n, dinv, w.p, w.ap, w.p2, w.s, x, w.r, w.state, w.partials,
-                                                          history, nullptr);
+                                                          history, nullptr, PeerKey{});
     } else {
-      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials, nullptr);
-      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history, nullptr);
+      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials, nullptr, PeerKey{});
+      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history, nullptr, PeerKey{});
     }
     return r;
   };

@@ -69,9 +69,27 @@ struct PeerView {
 static_assert(sizeof(PeerView) <= kCommHeaderBytes - kCommViewOffset, "PeerView fits the header page");
 
 __device__ __forceinline__ long long peer_tag(const PeerView& pv, long long k) { return (pv.epoch << 32) | (k + 1); }
+
+// What a kernel needs at its very start, passed BY VALUE as a kernel argument: polling the own slot
+// array through the PeerView in device memory costs three dependent loads (view -> header pointer ->
+// slot) before the first poll, on the critical path of every iteration.
+struct PeerKey {
+  CommHeader* own;   // this rank's header (local memory)
+  long long epoch;
+  int world, rank;
+  int lower_tiles, upper_tiles;  // SpMV tiles next to the lower / upper slab face, 0 without that neighbour
+  int has_lower, has_upper;
+};
+__device__ __forceinline__ long long peer_tag(const PeerKey& key, long long k) { return (key.epoch << 32) | (k + 1); }
+// Host-side bundle handed down the launch chain: the view in device memory (targets of the publishes
+// and of the halo stores) and the key.  nullptr = single GPU.
+struct PeerLaunch {
+  const PeerView* view;
+  PeerKey key;
+};
 // A peer never delivered: stop the solve with FEA_ERR_PEER instead of hanging the GPU.
-__device__ __forceinline__ void peer_failure(const PeerView& pv, PcgState* st) {
-  pv.hdr[pv.rank]->error = 1;
+__device__ __forceinline__ void peer_failure(const PeerKey& pv, PcgState* st) {
+  pv.own->error = 1;
   st->status = FEA_ERR_PEER;
   st->done = 1;
   st->rr_final = st->rr;
@@ -90,12 +108,12 @@ __device__ __forceinline__ void peer_publish(const PeerView& pv, int kind, long 
 }
 // One full warp: waits for every rank's slot of exchange (kind, k) in the own header and returns the
 // rank-ordered sums in all lanes; false if a peer never arrived.
-__device__ __forceinline__ bool peer_collect(const PeerView& pv, int kind, long long k, double& s0, double& s1) {
+__device__ __forceinline__ bool peer_collect(const PeerKey& pv, int kind, long long k, double& s0, double& s1) {
   const int lane = threadIdx.x & 31;
   double v0 = 0.0, v1 = 0.0;
   bool ok = true;
   if (lane < pv.world) {
-    const PeerSlot* src = &pv.hdr[pv.rank]->slots[(int)(k & 1)][kind][lane];
+    const PeerSlot* src = &pv.own->slots[(int)(k & 1)][kind][lane];
     ok = spin_until(&src->tag, peer_tag(pv, k), false);
     v0 = ld_volatile_f64(&src->v[0]);
     v1 = ld_volatile_f64(&src->v[1]);
@@ -125,7 +143,7 @@ inline unsigned vec_blocks(int64_t n) {
 // One full warp, two exchanges polled at once: lanes [0, world) wait for exchange (kind_a, ka), lanes
 // [kMaxPeers, kMaxPeers + world) for (kind_b, kb) (skipped when kb < 0).  a0 = sum of v[0] of the first,
 // b0 / b1 = sums of v[0] / v[1] of the second, all in rank order, in all lanes.
-__device__ __forceinline__ bool peer_collect2(const PeerView& pv, int kind_a, long long ka, int kind_b, long long kb,
+__device__ __forceinline__ bool peer_collect2(const PeerKey& pv, int kind_a, long long ka, int kind_b, long long kb,
                                               double& a0, double& b0, double& b1) {
   static_assert(2 * kMaxPeers <= 32, "two exchanges fit one warp");
   const int lane = threadIdx.x & 31;
@@ -136,7 +154,7 @@ __device__ __forceinline__ bool peer_collect2(const PeerView& pv, int kind_a, lo
   bool ok = true;
   if (mine) {
     const long long k = second ? kb : ka;
-    const PeerSlot* src = &pv.hdr[pv.rank]->slots[(int)(k & 1)][second ? kind_b : kind_a][src_rank];
+    const PeerSlot* src = &pv.own->slots[(int)(k & 1)][second ? kind_b : kind_a][src_rank];
     ok = spin_until(&src->tag, peer_tag(pv, k), false);
     v0 = ld_volatile_f64(&src->v[0]);
     v1 = ld_volatile_f64(&src->v[1]);
@@ -156,13 +174,14 @@ __device__ __forceinline__ bool peer_collect2(const PeerView& pv, int kind_a, lo
 // peer ranks inside these kernels and the direction kernel pushes the halo rows (see p2p.cu).
 __global__ void __launch_bounds__(256) pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ p,
                                   const double* __restrict__ ap, double* __restrict__ x, double* __restrict__ r,
-                                  PcgState* st, double* partials, const PeerView* pv);
+                                  PcgState* st, double* partials, const PeerView* pv, PeerKey key);
 __global__ void __launch_bounds__(256) pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
-                                     double* __restrict__ p, PcgState* st, double* history, const PeerView* pv);
+                                     double* __restrict__ p, PcgState* st, double* history, const PeerView* pv,
+                                     PeerKey key);
 __global__ void __launch_bounds__(256, 3) pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__ u,
                                 const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s,
                                 double* __restrict__ x, double* __restrict__ r, PcgState* st, double* partials,
-                                double* history, const PeerView* pv);
+                                double* history, const PeerView* pv, PeerKey key);
 __global__ void __launch_bounds__(256) pcg_init_kernel(int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
                                 double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, double tol,
                                 int max_iter, PcgState* st, double* partials);
@@ -170,7 +189,7 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(int64_t n, const double* 
 // step 1 (ap = K p over `n_nodes` rows, p.ap into state) on the best available kernel.
 int pcg_step_spmv(int d, int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
                   const double* p, double* ap, int64_t p_row_offset, PcgState* st, double* partials,
-                  cudaStream_t stream, const TmaPlan* plan, const PeerView* pv = nullptr);
+                  cudaStream_t stream, const TmaPlan* plan, const PeerLaunch* peer = nullptr);
 void pcg_match_carveout();
 // 0: classical PCG (3 kernels, 2 reductions per iteration); 1: single-reduction variant (2 kernels).
 // FEA_PCG_ALGO=0|1 overrides the automatic choice (see pcg.cu).

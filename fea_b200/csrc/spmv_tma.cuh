@@ -30,6 +30,8 @@
 // tile = blockIdx + gridDim * q, so the chip sweeps one contiguous window of the matrix and of
 // x at a time.
 #pragma once
+#include <type_traits>
+
 #include "spmv.cuh"
 
 namespace fea {
@@ -148,12 +150,13 @@ __device__ __forceinline__ TileRange tile_range(int r0, int r1, int total_cols) 
 // this rank's x by the neighbours' vector kernels over NVLink, followed by a tag.  Only the tiles
 // next to a slab face gather such rows, so the sweep starts `lower_tiles` tiles in (interior first;
 // the lower-face tiles wrap around to the very end) and a consumer group only looks at the tag right
-// before its first boundary tile: the halo exchange hides behind the interior of the SpMV.  The gated
-// kernel gathers x with ordinary loads, not ld.global.nc (see row_part_dot).
-struct HaloGate {
+// before its first boundary tile: the halo exchange hides behind the interior of the SpMV.  Face tiles
+// gather x through L2, not through the read-only path (see row_part_dot).
+struct HaloGate {  // a kernel argument (by value): every field is known to the host
   const long long* tag_lower;  // this rank's halo_tag[0] / [1]; nullptr without that neighbour
   const long long* tag_upper;
-  long long want;              // tag value of the iteration being multiplied
+  const int* iter;             // PcgState::iter: the tag to wait for is (epoch << 32 | *iter + 1)
+  long long epoch;
   int lower_tiles;             // tiles [0, lower_tiles) gather lower-halo rows
   int upper_tiles;             // tiles [n_tiles - upper_tiles, n_tiles) gather upper-halo rows
   int* error;                  // set to 1 when a neighbour never delivers
@@ -161,12 +164,13 @@ struct HaloGate {
 
 // A consumer group is about to start its face tiles: its leader polls the neighbours' tags, then the
 // group's named barrier orders every thread of the group after the acquire.
-__device__ __forceinline__ void halo_gate_wait(const HaloGate* gate, bool leader, int barrier_id, int barrier_threads) {
+__device__ __forceinline__ void halo_gate_wait(const HaloGate& gate, bool leader, int barrier_id, int barrier_threads) {
   if (leader) {
+    const long long want = (gate.epoch << 32) | ((long long)*gate.iter + 1);
     bool ok = true;
-    if (gate->tag_lower != nullptr) ok = spin_until(gate->tag_lower, gate->want, true) && ok;
-    if (gate->tag_upper != nullptr) ok = spin_until(gate->tag_upper, gate->want, true) && ok;
-    if (!ok) *gate->error = 1;
+    if (gate.tag_lower != nullptr) ok = spin_until(gate.tag_lower, want, true) && ok;
+    if (gate.tag_upper != nullptr) ok = spin_until(gate.tag_upper, want, true) && ok;
+    if (!ok) *gate.error = 1;
   }
   group_barrier(barrier_id, barrier_threads);
 }
@@ -174,13 +178,12 @@ __device__ __forceinline__ void halo_gate_wait(const HaloGate* gate, bool leader
 // Component b of one DOF row against x: sum_k vrow[D*k + b] * x[D*cols[k] + b].
 // `vrow` / `cols` may point to shared or global memory.  Every gather of a round is issued
 // before the first FMA.
-// WEAK: gather with ordinary (coherent-path) global loads instead of the read-only path.  The
-// multi-GPU kernel needs it: halo rows of x are written by the neighbour GPUs while the kernel runs,
-// which ld.global.nc must never see.  Ordinary loads are covered by the memory model: they follow the
-// tag's ld.acquire.sys (+ bar.sync) in causality order, so they observe the neighbours' stores (the
-// acquire drops stale L1 lines, e.g. a 128-byte line straddling the owned / halo border that an
-// interior tile pulled in earlier); they are cached in L1 like the read-only ones.
-template <int D, bool WEAK = false>
+// COHERENT: gather through L2 (ld.global.cg) instead of the read-only path.  The FACE tiles of a
+// multi-GPU slab need it: halo rows of x are written by the neighbour GPUs while the kernel runs, which
+// ld.global.nc must never see, and a 128-byte line straddling the owned / halo border may already sit
+// in L1 from an interior tile.  Interior tiles keep the read-only path (measured on one GPU: ordinary
+// or L2 loads for EVERY tile cost the SpMV 7-10 %).
+template <int D, bool COHERENT = false>
 __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t* cols, int cnt, int b,
                                                const double* x) {
   double acc = 0.0;
@@ -191,8 +194,8 @@ __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t
 #pragma unroll
     for (int u = 0; u < kTmaUnroll; ++u) {
       const int k = k0 + u;
-      if (WEAK)
-        xv[u] = k < cnt ? xb[(int64_t)D * cols[k]] : 0.0;
+      if (COHERENT)
+        xv[u] = k < cnt ? __ldcg(xb + (int64_t)D * cols[k]) : 0.0;
       else
         xv[u] = k < cnt ? __ldg(xb + (int64_t)D * cols[k]) : 0.0;
     }
@@ -212,7 +215,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
                                               const double* __restrict__ values, const double* x,
                                               double* __restrict__ y, const double* x_own, int stages,
                                               int val_cap, int col_cap, unsigned char* smem, double& dot,
-                                              const HaloGate* gate = nullptr) {
+                                              const HaloGate& gate = HaloGate{}) {
   constexpr int DD = D * D;
   constexpr int ROWS = D * kTileNodes;  // rows per tile
   constexpr int ITEMS = tma_items(D);   // (row, b) pairs per tile
@@ -237,7 +240,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
   const int total_cols = node_rowptr[n_nodes];
   const int stride = (int)gridDim.x;
   // sweep position t -> tile: rotated by the lower-face tiles when gated (interior first)
-  const int lower_tiles = GATED ? gate->lower_tiles : 0, upper_tiles = GATED ? gate->upper_tiles : 0;
+  const int lower_tiles = GATED ? gate.lower_tiles : 0, upper_tiles = GATED ? gate.upper_tiles : 0;
   const int rot = lower_tiles;
   auto tile_of = [&](int64_t t) -> int {
     const int64_t p = t + rot;
@@ -309,7 +312,8 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
     // positions and then over the face tiles, with the halo wait BETWEEN the two runs.  (With the wait --
     // a spin loop and a named barrier, inlined or not -- inside the loop, ptxas took the kernel from 50 to
     // 80 registers plus spills: 2 resident CTAs per SM instead of 3.)
-    auto sweep = [&](int64_t limit) {
+    auto sweep = [&](int64_t limit, auto coherent_tag) {
+    constexpr bool COHERENT = decltype(coherent_tag)::value;
     for (; tile64 < limit; q += G) {
       const int tile = tile_of(tile64);
       const int n0 = tile * kTileNodes;
@@ -334,7 +338,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
       if (t.direct) {
         if (active) {
           const double* vg = values + (int64_t)DD * lo + a * D * cnt;
-          part = row_part_dot<D, GATED>(vg, node_colidx + lo, cnt, b, x);
+          part = row_part_dot<D, COHERENT>(vg, node_colidx + lo, cnt, b, x);
         }
       } else {
         const int s = q % stages;
@@ -344,7 +348,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
           const unsigned char* buf = stage0 + (size_t)s * stage_bytes;
           const double* vs = reinterpret_cast<const double*>(buf) + (int)((int64_t)DD * lo - t.v_lo);
           const int32_t* cs = reinterpret_cast<const int32_t*>(buf + sizeof(double) * val_cap) + (lo - t.c_lo);
-          part = row_part_dot<D, GATED>(vs + a * D * cnt, cs, cnt, b, x);
+          part = row_part_dot<D, COHERENT>(vs + a * D * cnt, cs, cnt, b, x);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -369,13 +373,13 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
     if (GATED) {
       // sweep positions [0, n_tiles - lower - upper) are interior tiles, then the upper face, then the
       // lower face (rotation above); a group that owns face tiles waits for both neighbours once
-      sweep(n_tiles - lower_tiles - upper_tiles);
+      sweep(n_tiles - lower_tiles - upper_tiles, std::false_type{});
       if (tile64 < n_tiles) {  // group-uniform
         halo_gate_wait(gate, warp == group * GW && lane == 0, 1 + group, GW * 32);
-        sweep(n_tiles);
+        sweep(n_tiles, std::true_type{});
       }
     } else {
-      sweep(n_tiles);
+      sweep(n_tiles, std::false_type{});
     }
   }
 }

@@ -53,10 +53,16 @@ def uniform_load_vector(q_load: float, n: int, le: float) -> np.ndarray:
 
 
 def solve_beam(elements, EI, lengths, constraints, loads, tol: float = 1e-12, max_iter: int | None = None,
-               return_matrix: bool = False):
+               return_matrix: bool = False, method: str = "direct", extended: bool = True):
     """Assemble (euler_bernoulli.py:42-49), eliminate constrained DOF (:61-66), solve (:69),
     expand (:72-73).  elements (M,2); EI, lengths (M,); constraints, loads (n_nodes, 2).
-    Returns u (n_nodes, 2) [, BlockCSR, SolveInfo]."""
+    Returns u (n_nodes, 2) [, BlockCSR, SolveInfo].
+
+    method "direct" (default): block-tridiagonal parallel cyclic reduction on the device
+    (fea_chain_solve) -- the counterpart of the reference's dense LU (`np.linalg.solve`,
+    euler_bernoulli.py:69), eliminating in double-double arithmetic unless extended=False; it needs a
+    chain mesh (element i joins nodes i and i+1 in any order) and falls back to "pcg" otherwise.  method "pcg": Jacobi-PCG, usable while cond(K) ~ 5 n^4 stays far
+    below 1/eps (n of a few hundred)."""
     elements_d = core.to_device(elements, torch.int32)
     EI_d = core.to_device(EI, torch.float64)
     L_d = core.to_device(lengths, torch.float64)
@@ -64,7 +70,13 @@ def solve_beam(elements, EI, lengths, constraints, loads, tol: float = 1e-12, ma
     fixed = core._fixed_mask(constraints, 2 * n_nodes_)
     b = core.to_device(loads, torch.float64).reshape(-1)
     K = core.assemble_beam(EI_d, L_d, elements_d, n_nodes_, fixed=fixed)
-    u, info = core.pcg(K, b, tol=tol, max_iter=max_iter)
+    if method == "direct" and K.pattern.max_coupled <= 3:
+        try:
+            u, info = core.chain_solve(K, b, extended=extended)
+        except ValueError:  # three couplings per node, but not a chain
+            u, info = core.pcg(K, b, tol=tol, max_iter=max_iter)
+    else:
+        u, info = core.pcg(K, b, tol=tol, max_iter=max_iter)
     u_host = u.cpu().numpy().reshape(n_nodes_, 2)
     if return_matrix:
         return u_host, K, info

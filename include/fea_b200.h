@@ -290,6 +290,21 @@ int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t dof_per_node, const int32_t
                       void* work, size_t work_bytes, double* history, const fea_peer_comm* comm,
                       fea_pcg_result* result_host, void* stream);
 
+/* Direct solve of a CHAIN mesh (every node couples to its two neighbours only: the Euler-Bernoulli beam
+ * of euler_bernoulli.py:42-73, dof_per_node = 2; or 1): block-tridiagonal parallel cyclic reduction,
+ * ceil(log2 n) steps, replaces `np.linalg.solve` (euler_bernoulli.py:69) where Jacobi-PCG cannot
+ * (cond(K) ~ n^4).  `fixed` (uint8 per DOF, may be NULL) marks the homogeneous constraints
+ * (euler_bernoulli.py:61-66): x is exactly 0 there.  status = {FEA_ERR_INVALID, node} if the pattern is
+ * not a chain, {FEA_ERR_BREAKDOWN, node} for a singular pivot block (under-constrained beam).
+ * extended != 0: the elimination runs in double-double arithmetic (~106 bits) on the same FP64 matrix
+ * and right-hand side, x is rounded back to FP64 -- cond(K) ~ 5 n^4 reaches 5e20 at the 100 k elements
+ * of BASELINE config 2, where FP64 elimination returns noise. */
+size_t fea_chain_solve_workspace(int64_t n_nodes, int32_t dof_per_node, int32_t extended);
+int fea_chain_solve(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
+                    const int32_t* node_colidx, const double* values, const uint8_t* fixed,
+                    const double* b, double* x, int32_t extended, void* work, size_t work_bytes,
+                    int32_t* status, void* stream);
+
 /* Batched multi-RHS Jacobi-PCG (BASELINE config 5): n_rhs <= 256 independent systems sharing K,
  * each column with its own alpha/beta and stopping rule.  B, X: (n_dof, n_rhs) row-major.
  * iterations_host [n_rhs] (HOST, may be NULL): iterations each column needed.
