@@ -142,13 +142,15 @@ struct BeamOp {
   const double* length;
   __device__ void block(int64_t e, int a, int b, double out[2][2], int32_t*) const {
     const double L = length[e];
-    const double c = EI[e] / (L * L * L);  // euler_bernoulli.py:22-39
+    const double c = EI[e] / cube_rn(L);  // euler_bernoulli.py:22-39
     const double s = 6.0 * L, f = 4.0 * (L * L), h = 2.0 * (L * L);
     const double m[4][4] = {{12.0, s, -12.0, s}, {s, f, -s, h}, {-12.0, -s, 12.0, -s}, {s, h, -s, f}};
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) out[r][cc] = c * m[2 * a + r][2 * b + cc];
+      for (int cc = 0; cc < 2; ++cc)
+        out[r][cc] = __dmul_rn(c, m[2 * a + r][2 * b + cc]);  // rounded like the reference's Ke entry: the caller's
+                                                              // accumulation must not fuse it into an FMA (cond ~ n^4)
   }
 };
 

@@ -132,6 +132,17 @@ __device__ __forceinline__ bool spin_until(const long long* p, long long want, b
   return false;
 }
 
+// x^3 rounded once (to within a double-rounding tie of the correctly rounded cube), like libm's pow(x, 3)
+// that the reference's `element_length**3` calls (euler_bernoulli.py:22).  x*x*x rounds twice and lands an
+// ulp away about every third argument; harmless at 1e-10 -- but the Hermite beam matrix has cond ~ 5 n^4,
+// and at 100 k elements the LAST BIT of its entries decides whether the exact solution of the assembled
+// matrix is 1e-5 or 3e-2 away from the analytic deflection (tests: test_beam_chain_solver_at_size).
+__device__ __forceinline__ double cube_rn(double x) {
+  const double p = __dmul_rn(x, x), pe = __fma_rn(x, x, -p);      // x^2 = p + pe exactly
+  const double q = __dmul_rn(p, x), qe = __fma_rn(p, x, -q);      // p x = q + qe exactly
+  return __dadd_rn(q, __dadd_rn(qe, __dmul_rn(pe, x)));
+}
+
 // Streaming (evict-first) loads for data read exactly once per kernel: keeps L2 for the vectors.
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }

@@ -75,7 +75,7 @@ __global__ void ke_beam_kernel(const double* __restrict__ EI, const double* __re
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_elem) return;
   const double L = length[e];
-  const double c = EI[e] / (L * L * L);  // euler_bernoulli.py:22
+  const double c = EI[e] / cube_rn(L);  // euler_bernoulli.py:22
   const double s = 6.0 * L, f = 4.0 * (L * L), h = 2.0 * (L * L);
   const double m[16] = {12.0, s, -12.0, s, s, f, -s, h, -12.0, -s, 12.0, -s, s, h, -s, f};
   double* out = ke + e * 16;

@@ -9,14 +9,16 @@
 // which stay the only launches of the CUDA graph:
 //
 //   SpMV       interior tiles first; a consumer group looks at the neighbours' halo tags only right
-//              before its first face tile (HaloGate, spmv_tma.cuh), so the halo exchange hides behind
-//              the interior of the slab.  Last block: publish this rank's p.Ap to every rank's slot
-//              array (one warp, NVLink stores)
+//              before its first face tile (HaloGate, spmv_tma.cuh).  Last block: publish this rank's
+//              p.Ap to every rank's slot array (one warp, NVLink stores, flag-in-word: no fences)
 //   update     every CTA: collect the world's p.Ap from the own slot array (local L2 polls), add
 //              in rank order -> alpha; last block: publish (r.z, r.r)
-//   direction  every CTA: collect (r.z, r.r) -> beta / convergence; the boundary rows of the new p
-//              are stored straight into the neighbours' halo rows while p is written; last block:
-//              release the iteration tag to the neighbours (nobody waits at a kernel boundary)
+//   direction  every CTA: collect (r.z, r.r) -> beta / convergence; new p
+//   halo push  on a SIDE stream, concurrent with the next SpMV's interior tiles: the boundary rows of
+//              the new p go into the neighbours' halo rows (NVLink stores), then ONE system fence and
+//              the iteration tag.  Everything that needs system-scope ordering lives here, off the
+//              critical path: measured on one GPU, a __threadfence_system costs ~5 us, and with the
+//              stores and the tag inside the vector kernel it sat in every iteration's dependency chain.
 // (single-reduction recurrence: update + direction are one kernel, one reduction per iteration.)
 //
 // Every rank forms bitwise identical sums (rank order, no atomics), hence identical convergence
@@ -244,6 +246,7 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   PeerLaunch peer;
   peer.view = pv_dev;
   peer.key.own = pv.hdr[pv.rank];
+  for (int i = 0; i < kMaxPeers; ++i) peer.key.hdr[i] = pv.hdr[i];
   peer.key.epoch = pv.epoch;
   peer.key.world = pv.world;
   peer.key.rank = pv.rank;
@@ -263,12 +266,34 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     for (int i = 0; i < 2 * kMaxSamples; ++i) cudaEventCreate(&sample_ev[i]);
   }
   int64_t enqueued = 0;
+  // side stream of the halo push: forks after the vector kernel(s), joins before the next ones
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool join_pending = false;
+  if (rc == FEA_OK && multi) {
+    rc = check(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    if (rc == FEA_OK) rc = check(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    if (rc == FEA_OK) rc = check(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  auto join_side = [&]() {  // the vector kernels overwrite the rows the push is still reading
+    if (join_pending) cudaStreamWaitEvent(stream, ev_join, 0);
+    join_pending = false;
+  };
+  auto fork_halo = [&]() {
+    if (!multi) return;
+    cudaEventRecord(ev_fork, stream);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+    p2p_halo_kernel<<<halo_blocks, 256, 0, side>>>(pv, state);
+    cudaEventRecord(ev_join, side);
+    join_pending = true;
+  };
   auto iteration = [&](bool sample) -> int {
     if (sample) sample_iter[n_samples] = (int)enqueued;
     if (sample) cudaEventRecord(sample_ev[2 * n_samples], stream);
     const int r1 = pcg_step_spmv(d, n_owned_nodes, node_rowptr_owned, node_colidx, values, p_ext, ap,
                                  comm->own_offset_nodes, state, partials, stream, &plan, peer_it);
     if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
+    join_side();
     if (algo == 1) {  // p_own holds u = dinv r here (the SpMV input)
       pcg_cgcg_kernel<<<cgcg_blocks(n), 256, 0, stream>>>(n, dinv, p_own, ap, p2, s_vec, x, r, state, partials, history,
                                                           pv_it, peer.key);
@@ -276,9 +301,10 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
       pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, p_own, ap, x, r, state, partials, pv_it, peer.key);
       pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, r, p_own, state, history, pv_it, peer.key);
     }
+    fork_halo();
     return r1;
   };
-  const int launches_per_iteration = algo == 1 ? 2 : 3;
+  const int launches_per_iteration = (algo == 1 ? 2 : 3) + (multi ? 1 : 0);
   const int64_t enqueue_limit = (int64_t)max_iter + (algo == 1 ? 1 : 0);
 
   if (rc == FEA_OK) {
@@ -299,11 +325,13 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   bool finished = false;
   if (rc == FEA_OK && max_iter >= chunk && std::getenv("FEA_PCG_NO_GRAPH") == nullptr) {
     rc = iteration(false);  // warm-up outside capture
+    join_side();
     if (rc == FEA_OK) rc = check_launch(launches_per_iteration);
     enqueued += 1;
     cudaGraph_t graph = nullptr;
     if (rc == FEA_OK && cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
       for (int it = 0; it < chunk - 1; ++it) iteration(false);
+      join_side();  // the side stream must rejoin the capturing stream before the capture ends
       if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || graph == nullptr ||
           cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess)
         graph_exec = nullptr;
@@ -315,6 +343,7 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     const int todo = (int)std::min<int64_t>(chunk, enqueue_limit - enqueued);
     if (graph_exec != nullptr && todo == chunk) {  // one plain iteration (carries the timing sample) + the graph
       rc = iteration(sample_ev != nullptr && n_samples < kMaxSamples);
+      join_side();
       if (rc == FEA_OK) rc = check(cudaGraphLaunch(graph_exec, stream));
     } else {
       for (int it = 0; it < todo && rc == FEA_OK; ++it)
@@ -337,10 +366,12 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     if (!finished && enqueued >= enqueue_limit) finished = true;
     slot ^= 1;
   }
+  join_side();
   if (rc == FEA_OK) {
     rc = check(cudaMemcpyAsync(&snap[0], state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
     if (rc == FEA_OK) rc = check(cudaStreamSynchronize(stream));
   }
+  if (side != nullptr) cudaStreamSynchronize(side);
   if (rc == FEA_OK) {
     const PcgState& s = snap[0];
     result_host->iterations = s.iter;
@@ -365,6 +396,9 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     delete[] sample_ev;
   }
   if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
+  if (side != nullptr) cudaStreamDestroy(side);
+  for (cudaEvent_t e : {ev_fork, ev_join})
+    if (e != nullptr) cudaEventDestroy(e);
   if (stream != nullptr) {
     if (ev_order != nullptr && cudaEventRecord(ev_order, stream) == cudaSuccess) cudaStreamWaitEvent(caller, ev_order, 0);
     cudaStreamDestroy(stream);

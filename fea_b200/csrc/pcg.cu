@@ -90,12 +90,18 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
 }
 
 // Block partial -> global slot; returns true in the last block to finish (all threads).
+// `sys`: the block also stored rows into a peer GPU's memory; its leader fences at system scope (one
+// fence per block, after the block-wide barrier of block_sum, instead of one per thread) so that the
+// tag the LAST block releases afterwards is ordered behind every block's NVLink stores.
 __device__ __forceinline__ bool publish_partials(double* partials, int n_scalars, const double* vals,
-                                                 uint32_t* counter) {
+                                                 uint32_t* counter, bool sys = false) {
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_scalars; ++s) partials[s * kMaxPartials + blockIdx.x] = vals[s];
-    __threadfence();
+    if (sys)
+      __threadfence_system();
+    else
+      __threadfence();
     const uint32_t ticket = atomicAdd(counter, 1u);
     s_last = ticket == gridDim.x - 1;
   }
@@ -122,7 +128,7 @@ __device__ __forceinline__ void finish_pap(const double* partials, double* s_red
   if (pv != nullptr) {
     __syncthreads();
     if (threadIdx.x == 0 && key.own->error != 0) peer_failure(key, st);  // a halo gate timed out
-    if (threadIdx.x < 32) peer_publish(*pv, 1, st->iter, s_red[0], 0.0);
+    if (threadIdx.x < 32) peer_publish(key, 1, st->iter, s_red[0], 0.0);
   }
 }
 
@@ -416,7 +422,7 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
     }
     if (pv != nullptr) {
       __syncthreads();
-      if (threadIdx.x < 32) peer_publish(*pv, 2, iter, s_glob[0], s_glob[1]);
+      if (threadIdx.x < 32) peer_publish(key, 2, iter, s_glob[0], s_glob[1]);
     }
   }
 }
@@ -455,34 +461,19 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
     const double beta = rz_new / rz;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pv == nullptr) {
-      for (; i + 3 * stride < n; i += 4 * stride) {
-        double di[4], ri[4], pi[4];
+    for (; i + 3 * stride < n; i += 4 * stride) {
+      double di[4], ri[4], pi[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int64_t j = i + u * stride;
-          di[u] = dinv[j];
-          ri[u] = r[j];
-          pi[u] = p[j];
-        }
+      for (int u = 0; u < 4; ++u) {
+        const int64_t j = i + u * stride;
+        di[u] = dinv[j];
+        ri[u] = r[j];
+        pi[u] = p[j];
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) p[i + u * stride] = fma(beta, pi[u], di[u] * ri[u]);
-      }
-      for (; i < n; i += stride) p[i] = fma(beta, p[i], dinv[i] * r[i]);
-    } else {
-      // the boundary rows of the new p also go straight into the neighbours' halo rows (NVLink stores)
-      const long long lo_off = pv->lower_off, lo_cnt = pv->lower >= 0 ? pv->lower_cnt : 0;
-      const long long up_off = pv->upper_off, up_cnt = pv->upper >= 0 ? pv->upper_cnt : 0;
-      double* lo_dst = pv->lower_dst;
-      double* up_dst = pv->upper_dst;
-      for (; i < n; i += stride) {
-        const double v = fma(beta, p[i], dinv[i] * r[i]);
-        p[i] = v;
-        if ((unsigned long long)(i - lo_off) < (unsigned long long)lo_cnt) lo_dst[i - lo_off] = v;
-        if ((unsigned long long)(i - up_off) < (unsigned long long)up_cnt) up_dst[i - up_off] = v;
-      }
-      __threadfence_system();
+      for (int u = 0; u < 4; ++u) p[i + u * stride] = fma(beta, pi[u], di[u] * ri[u]);
     }
+    for (; i < n; i += stride) p[i] = fma(beta, p[i], dinv[i] * r[i]);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -512,15 +503,7 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
       }
     }
     st->counter[2] = 0;
-    if (pv != nullptr && !finished) {
-      // every block's halo stores are fenced (above) and counted: release the iteration tag to the
-      // neighbours.  Nobody waits here: the next SpMV looks at the neighbours' tags right before its
-      // first face tile (HaloGate, spmv_tma.cuh), after the interior of the slab.
-      const long long tag = peer_tag(*pv, iter);
-      __threadfence_system();
-      if (pv->lower >= 0) st_release_sys(&pv->hdr[pv->lower]->halo_tag[1], tag);  // I am its upper neighbour
-      if (pv->upper >= 0) st_release_sys(&pv->hdr[pv->upper]->halo_tag[0], tag);
-    }
+    (void)finished;  // multi-GPU: the boundary rows of the new p travel in p2p_halo_kernel, on a side stream
   }
 }
 
@@ -601,10 +584,6 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
   }
   double s_ru = 0.0, s_rr = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const long long lo_off = pv ? pv->lower_off : 0, lo_cnt = pv && pv->lower >= 0 ? pv->lower_cnt : 0;
-  const long long up_off = pv ? pv->upper_off : 0, up_cnt = pv && pv->upper >= 0 ? pv->upper_cnt : 0;
-  double* lo_dst = pv ? pv->lower_dst : nullptr;
-  double* up_dst = pv ? pv->upper_dst : nullptr;
   auto finish = [&](int64_t j, double di, double uj, double wj, double pj, double sj, double xj, double rj) {
     const double pn = iter == 0 ? uj : fma(beta, pj, uj);
     const double sn = iter == 0 ? wj : fma(beta, sj, wj);
@@ -615,10 +594,6 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
     __stcs(x + j, fma(alpha, pn, xj));
     r[j] = rn;
     u[j] = un;
-    if (pv != nullptr) {  // boundary rows of the new u go straight into the neighbours' halo rows
-      if ((unsigned long long)(j - lo_off) < (unsigned long long)lo_cnt) lo_dst[j - lo_off] = un;
-      if ((unsigned long long)(j - up_off) < (unsigned long long)up_cnt) up_dst[j - up_off] = un;
-    }
     if (di != 0.0) {
       s_ru = fma(rn, un, s_ru);
       s_rr = fma(rn, rn, s_rr);
@@ -641,7 +616,6 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
   }
   for (; i < n; i += stride)
     finish(i, dinv[i], u[i], w[i], iter != 0 ? p[i] : 0.0, iter != 0 ? s[i] : 0.0, x[i], r[i]);
-  if (pv != nullptr) __threadfence_system();
   double tot[2];
   tot[0] = block_sum(s_ru, s_red);
   tot[1] = block_sum(s_rr, s_red);
@@ -662,14 +636,7 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
     }
     if (pv != nullptr) {
       __syncthreads();
-      if (threadIdx.x < 32) peer_publish(*pv, 2, iter, s_glob[0], s_glob[1]);
-      if (threadIdx.x == 0) {
-        const long long tag = peer_tag(*pv, iter + 1);
-        __threadfence_system();
-        if (pv->lower >= 0) st_release_sys(&pv->hdr[pv->lower]->halo_tag[1], tag);
-        if (pv->upper >= 0) st_release_sys(&pv->hdr[pv->upper]->halo_tag[0], tag);
-        // no wait here: the next SpMV gates its face tiles on the neighbours' tags (HaloGate)
-      }
+      if (threadIdx.x < 32) peer_publish(key, 2, iter, s_glob[0], s_glob[1]);
     }
   }
 }

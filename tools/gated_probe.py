@@ -28,8 +28,10 @@ ws = lib.fea_pcg_workspace(n)
 work = torch.empty(ws, dtype=torch.uint8, device="cuda")
 res = _lib.PcgResult()
 epoch = 0
-for algo in (0, 1):
-    for forced in ("0", "1", "0", "1"):
+only = os.environ.get("PROBE_ONLY")  # "algo,gated": a single variant (for ncu)
+variants = [(int(only.split(",")[0]), only.split(",")[1])] if only else [(a, f) for a in (0, 1) for f in ("0", "1", "0", "1")]
+for algo, forced in variants:
+    if True:
         os.environ["FEA_P2P_FORCE_GATED"] = forced
         epoch += 1
         desc = _lib.PeerComm()
