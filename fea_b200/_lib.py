@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_int32, c_int64, c_size_t, c_void_p
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libfea_b200.so")
+LIB_PATH = os.environ.get("FEA_LIB_PATH") or os.path.join(HERE, "csrc", "libfea_b200.so")
 
 FEA_OK = 0
 FEA_ERR_INVALID = 1

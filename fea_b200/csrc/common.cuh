@@ -131,6 +131,18 @@ __device__ __forceinline__ bool spin_until(const long long* p, long long want, b
   }
   return false;
 }
+// The same with exponential back-off (0.2 .. 3.2 us), for flags that MANY threads wait on at once: the
+// halo tags are polled by every CTA of the SpMV, and ~900 pollers at 10 MHz each saturate the one L2
+// slice that the neighbour's NVLink write of the very same tag has to get through.  ~2 s bound.
+__device__ __forceinline__ bool spin_until_backoff(const long long* p, long long want) {
+  unsigned ns = 200;
+  for (int i = 0; i < (1 << 20); ++i) {
+    if (ld_acquire_sys(p) >= want) return true;
+    __nanosleep(ns);
+    if (ns < 3200) ns *= 2;
+  }
+  return false;
+}
 
 // x^3 rounded once (to within a double-rounding tie of the correctly rounded cube), like libm's pow(x, 3)
 // that the reference's `element_length**3` calls (euler_bernoulli.py:22).  x*x*x rounds twice and lands an

@@ -28,6 +28,7 @@
 // i.e. after this rank's SpMV k (the reader of the old rows) has finished.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -82,10 +83,17 @@ __global__ void __launch_bounds__(32) p2p_init_exchange_kernel(PeerView pv, PcgS
 
 // Halo rows of the initial p (later iterations store them from inside the vector kernels); the tag
 // is released by the last block, nobody waits: the first SpMV gates its face tiles on it.
-__global__ void __launch_bounds__(256) p2p_halo_kernel(PeerView pv, PcgState* st) {
+// Small on purpose (blocks of 128 threads, <= 48 registers): during the iteration it runs NEXT TO the
+// persistent SpMV, which leaves 6400 registers and ~990 thread slots free per SM (3 CTAs x 11 warps x 56
+// registers).  A 256-thread block with 32 registers does not fit beside it and would only start once
+// SpMV CTAs exit -- which they do after their face tiles, which wait for this very kernel's tag on the
+// neighbour.
+constexpr int kHaloThreads = 128;
+__global__ void __launch_bounds__(kHaloThreads, 10) p2p_halo_kernel(PeerView pv, PcgState* st) {
   __shared__ bool s_last;
   if (st->done) return;
   const long long tag = peer_tag(pv, st->iter);
+  if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(pv.hdr[pv.rank], st->iter, 3);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pv.lower >= 0)
@@ -102,6 +110,7 @@ __global__ void __launch_bounds__(256) p2p_halo_kernel(PeerView pv, PcgState* st
   __threadfence_system();
   if (pv.lower >= 0) st_release_sys(&pv.hdr[pv.lower]->halo_tag[1], tag);  // I am its upper neighbour
   if (pv.upper >= 0) st_release_sys(&pv.hdr[pv.upper]->halo_tag[0], tag);
+  dbg_stamp(own, st->iter, 4);
 }
 
 }  // namespace fea
@@ -187,13 +196,24 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     const int64_t first_node = n_owned_nodes - std::min<int64_t>(std::max<int64_t>(comm->boundary_upper_nodes, 0), n_owned_nodes);
     pv.upper_tiles = comm->boundary_upper_nodes > 0 ? (int)(n_tiles - first_node / kTileNodes) : 0;
   }
-  if (pv.lower < 0) pv.lower_tiles = 0;
-  if (pv.upper < 0) pv.upper_tiles = 0;
+  if (std::getenv("FEA_P2P_FAKE_TILES") == nullptr) {  // (experiment: keep face tiles without neighbours)
+    if (pv.lower < 0) pv.lower_tiles = 0;
+    if (pv.upper < 0) pv.upper_tiles = 0;
+  }
   // experiment switches: FEA_HALO_GATE=0 waits for the halo before the FIRST tile (no
   // overlap, the round-1 behaviour moved into the SpMV); FEA_P2P_FORCE_GATED=1 runs the gated kernels on
   // a single rank too (A/B of the gated against the plain SpMV on one GPU)
   if (const char* env = std::getenv("FEA_HALO_GATE")) {
     if (env[0] == '0') pv.lower_tiles = pv.upper_tiles = (int)n_tiles;
+  }
+  const bool debug = std::getenv("FEA_P2P_DEBUG") != nullptr;
+  {
+    const int on = debug ? 1 : 0;
+    CommHeader* hdr0 = static_cast<CommHeader*>(comm->comm[comm->rank]);
+    cudaMemcpy(&hdr0->dbg_on, &on, sizeof(int), cudaMemcpyHostToDevice);
+    const unsigned long long lo = ~0ULL, hi = 0ULL;
+    cudaMemcpy(&hdr0->dbg_cta_first, &lo, sizeof(lo), cudaMemcpyHostToDevice);
+    cudaMemcpy(&hdr0->dbg_cta_last, &hi, sizeof(hi), cudaMemcpyHostToDevice);
   }
   const char* force_env = std::getenv("FEA_P2P_FORCE_GATED");
   const bool force_gated = force_env != nullptr && force_env[0] == '1';
@@ -236,17 +256,16 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   if (rc == FEA_OK) rc = check(cudaStreamWaitEvent(stream, ev_order, 0));
 
   const unsigned vb = vec_blocks(n);
-  const unsigned halo_blocks = 8;
+  const unsigned halo_blocks = 16;
   auto exchange = [&]() {
     if (multi) p2p_init_exchange_kernel<<<1, 32, 0, stream>>>(pv, state);
   };
   auto halo = [&]() {
-    if (multi) p2p_halo_kernel<<<halo_blocks, 256, 0, stream>>>(pv, state);
+    if (multi) p2p_halo_kernel<<<halo_blocks, kHaloThreads, 0, stream>>>(pv, state);
   };
   PeerLaunch peer;
   peer.view = pv_dev;
   peer.key.own = pv.hdr[pv.rank];
-  for (int i = 0; i < kMaxPeers; ++i) peer.key.hdr[i] = pv.hdr[i];
   peer.key.epoch = pv.epoch;
   peer.key.world = pv.world;
   peer.key.rank = pv.rank;
@@ -271,7 +290,15 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool join_pending = false;
   if (rc == FEA_OK && multi) {
-    rc = check(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    // The push must run WHILE the persistent SpMV owns every SM (3 CTAs each, nearly all shared memory):
+    // same shared-memory carve-out as the SpMV (an SM cannot hold two carve-outs at once: with the default
+    // preference the push only started once the SpMV had drained, and both ranks' face tiles sat waiting
+    // for each other's tag -- 705 us per SpMV instead of 440 at N = 2), and the highest stream priority so
+    // that its 8 small blocks are dispatched first.
+    cudaFuncSetAttribute(p2p_halo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    rc = check(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
     if (rc == FEA_OK) rc = check(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     if (rc == FEA_OK) rc = check(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   }
@@ -279,11 +306,17 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     if (join_pending) cudaStreamWaitEvent(stream, ev_join, 0);
     join_pending = false;
   };
+  const char* side_env = std::getenv("FEA_P2P_SIDE");  // experiment switch: 0 = push on the solver's own stream
+  const bool use_side = side_env == nullptr || side_env[0] != '0';
   auto fork_halo = [&]() {
     if (!multi) return;
+    if (!use_side) {
+      p2p_halo_kernel<<<halo_blocks, kHaloThreads, 0, stream>>>(pv, state);
+      return;
+    }
     cudaEventRecord(ev_fork, stream);
     cudaStreamWaitEvent(side, ev_fork, 0);
-    p2p_halo_kernel<<<halo_blocks, 256, 0, side>>>(pv, state);
+    p2p_halo_kernel<<<halo_blocks, kHaloThreads, 0, side>>>(pv, state);
     cudaEventRecord(ev_join, side);
     join_pending = true;
   };
@@ -372,6 +405,18 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
     if (rc == FEA_OK) rc = check(cudaStreamSynchronize(stream));
   }
   if (side != nullptr) cudaStreamSynchronize(side);
+  if (debug) {
+    unsigned long long h[8][6];
+    cudaMemcpy(h, pv.hdr[pv.rank]->dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < kDbgIters; ++i) {
+      const double t0 = (double)h[i][0];
+      std::fprintf(stderr,
+                   "[p2p dbg rank %d it %d] spmv_start 0  push_start %+.1f  push_done %+.1f  "
+                   "spmv_done %+.1f  next_spmv_start %+.1f us\n",
+                   pv.rank, kDbgFirst + i, ((double)h[i][3] - t0) * 1e-3, ((double)h[i][4] - t0) * 1e-3, ((double)h[i][5] - t0) * 1e-3,
+                   i + 1 < kDbgIters ? ((double)h[i + 1][0] - t0) * 1e-3 : 0.0);
+    }
+  }
   if (rc == FEA_OK) {
     const PcgState& s = snap[0];
     result_host->iterations = s.iter;

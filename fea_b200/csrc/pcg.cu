@@ -128,7 +128,8 @@ __device__ __forceinline__ void finish_pap(const double* partials, double* s_red
   if (pv != nullptr) {
     __syncthreads();
     if (threadIdx.x == 0 && key.own->error != 0) peer_failure(key, st);  // a halo gate timed out
-    if (threadIdx.x < 32) peer_publish(key, 1, st->iter, s_red[0], 0.0);
+    if (threadIdx.x == 0) dbg_stamp(key.own, st->iter, 5);
+    if (threadIdx.x < 32) peer_publish(*pv, 1, st->iter, s_red[0], 0.0);
   }
 }
 
@@ -217,6 +218,7 @@ pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const 
     gate.lower_tiles = key.lower_tiles;
     gate.upper_tiles = key.upper_tiles;
     gate.error = &key.own->error;
+    if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(key.own, st->iter, 0);
   }
   spmv_tma_body<D, G, true, GATED>(n_nodes, node_rowptr, node_colidx, values, p, ap, p_own, stages, val_cap, col_cap,
                                    s_tma, dot, gate);
@@ -422,7 +424,7 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
     }
     if (pv != nullptr) {
       __syncthreads();
-      if (threadIdx.x < 32) peer_publish(key, 2, iter, s_glob[0], s_glob[1]);
+      if (threadIdx.x < 32) peer_publish(*pv, 2, iter, s_glob[0], s_glob[1]);
     }
   }
 }
@@ -636,7 +638,7 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
     }
     if (pv != nullptr) {
       __syncthreads();
-      if (threadIdx.x < 32) peer_publish(key, 2, iter, s_glob[0], s_glob[1]);
+      if (threadIdx.x < 32) peer_publish(*pv, 2, iter, s_glob[0], s_glob[1]);
     }
   }
 }

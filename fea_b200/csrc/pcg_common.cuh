@@ -59,7 +59,22 @@ struct CommHeader {
   long long halo_tag[2];            // [0] written by the lower neighbour, [1] by the upper one
   unsigned int counter;             // last-block ticket of the halo kernel
   int error;
+  // FEA_P2P_DEBUG=1: %globaltimer stamps of iterations [kDbgFirst, kDbgFirst + kDbgIters):
+  // [it][0] SpMV start (block 0), [1] face wait begins, [2] face wait ends (block 0, group 0),
+  // [3] local halo push starts, [4] local halo push has released its tags, [5] SpMV last block done
+  unsigned long long dbg[8][6];
+  unsigned long long dbg_cta_first, dbg_cta_last;  // earliest / latest CTA start of the SpMV of iteration kDbgFirst
+  int dbg_on, dbg_pad;
 };
+constexpr int kDbgFirst = 200, kDbgIters = 8;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void dbg_stamp(CommHeader* own, int iter, int what) {
+  if (own->dbg_on && iter >= kDbgFirst && iter < kDbgFirst + kDbgIters) own->dbg[iter - kDbgFirst][what] = global_ns();
+}
 static_assert(sizeof(CommHeader) <= kCommViewOffset, "comm header");
 
 struct PeerView {
@@ -84,7 +99,6 @@ __device__ __forceinline__ long long peer_tag(const PeerView& pv, long long k) {
 // slot) before the first poll, on the critical path of every iteration.
 struct PeerKey {
   CommHeader* own;   // this rank's header (local memory)
-  CommHeader* hdr[kMaxPeers];  // every rank's header as mapped here (targets of the scalar publishes)
   long long epoch;
   int world, rank;
   int lower_tiles, upper_tiles;  // SpMV tiles next to the lower / upper slab face, 0 without that neighbour
@@ -117,7 +131,9 @@ __device__ __forceinline__ void ld_volatile_v2(const unsigned long long* p, unsi
   asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 // One full warp: lane r stores (v0, v1) + flag into rank r's slot for this rank (NVLink stores).
-__device__ __forceinline__ void peer_publish(const PeerKey& pv, int kind, long long k, double v0, double v1) {
+// (The peers' header pointers come from the PeerView in device memory, indexed by lane: as a by-value
+// kernel argument the indexed array went to local memory and took the SpMV from 50 to 98 registers.)
+__device__ __forceinline__ void peer_publish(const PeerView& pv, int kind, long long k, double v0, double v1) {
   const int lane = threadIdx.x & 31;
   if (lane < pv.world) {
     LlSlot* dst = &pv.hdr[lane]->ll[(int)(k & 1)][kind - 1][pv.rank];

@@ -168,8 +168,8 @@ __device__ __forceinline__ void halo_gate_wait(const HaloGate& gate, bool leader
   if (leader) {
     const long long want = (gate.epoch << 32) | ((long long)*gate.iter + 1);
     bool ok = true;
-    if (gate.tag_lower != nullptr) ok = spin_until(gate.tag_lower, want, true) && ok;
-    if (gate.tag_upper != nullptr) ok = spin_until(gate.tag_upper, want, true) && ok;
+    if (gate.tag_lower != nullptr) ok = spin_until_backoff(gate.tag_lower, want) && ok;
+    if (gate.tag_upper != nullptr) ok = spin_until_backoff(gate.tag_upper, want) && ok;
     if (!ok) *gate.error = 1;
   }
   group_barrier(barrier_id, barrier_threads);
@@ -194,9 +194,15 @@ __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t
 #pragma unroll
     for (int u = 0; u < kTmaUnroll; ++u) {
       const int k = k0 + u;
+#ifdef FEA_GATED_WEAK
+      if (COHERENT)
+        xv[u] = k < cnt ? xb[(int64_t)D * cols[k]] : 0.0;
+      else
+#else
       if (COHERENT)
         xv[u] = k < cnt ? __ldcg(xb + (int64_t)D * cols[k]) : 0.0;
       else
+#endif
         xv[u] = k < cnt ? __ldg(xb + (int64_t)D * cols[k]) : 0.0;
     }
 #pragma unroll
@@ -373,7 +379,11 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
     if (GATED) {
       // sweep positions [0, n_tiles - lower - upper) are interior tiles, then the upper face, then the
       // lower face (rotation above); a group that owns face tiles waits for both neighbours once
+#ifdef FEA_GATED_INTERIOR_CG
+      sweep(n_tiles - lower_tiles - upper_tiles, std::true_type{});
+#else
       sweep(n_tiles - lower_tiles - upper_tiles, std::false_type{});
+#endif
       if (tile64 < n_tiles) {  // group-uniform
         halo_gate_wait(gate, warp == group * GW && lane == 0, 1 + group, GW * 32);
         sweep(n_tiles, std::true_type{});

@@ -38,6 +38,8 @@ for algo, forced in variants:
         desc.world, desc.rank, desc.lower_peer, desc.upper_peer, desc.epoch = 1, 0, -1, -1, epoch
         desc.comm[0] = own.value
         desc.algo = algo
+        if os.environ.get("FEA_P2P_FAKE_TILES"):
+            desc.boundary_lower_nodes = desc.boundary_upper_nodes = (b + 1) ** 2 + b + 2
         lib.fea_profile_enable(1)
         a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
