@@ -273,6 +273,12 @@ extern "C" int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t d, const int32_t
   peer.key.upper_tiles = pv.upper_tiles;
   peer.key.has_lower = pv.lower >= 0;
   peer.key.has_upper = pv.upper >= 0;
+  {
+    const size_t lo_bytes = sizeof(double) * (size_t)d * (size_t)comm->own_offset_nodes;
+    const size_t hi_bytes = lo_bytes + sizeof(double) * (size_t)n;
+    peer.key.aligned = (reinterpret_cast<uintptr_t>(p_ext) % 128 == 0) && (pv.lower < 0 || lo_bytes % 128 == 0) &&
+                       (pv.upper < 0 || hi_bytes % 128 == 0) && std::getenv("FEA_HALO_COHERENT") == nullptr;
+  }
   const PeerLaunch* peer_it = multi || force_gated ? &peer : nullptr;
   const PeerView* pv_it = peer_it ? pv_dev : nullptr;
   // measurement hook (as in fea_pcg_solve): CUDA-event pairs around one SpMV launch per chunk

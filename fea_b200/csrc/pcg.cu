@@ -218,6 +218,7 @@ pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const 
     gate.lower_tiles = key.lower_tiles;
     gate.upper_tiles = key.upper_tiles;
     gate.error = &key.own->error;
+    gate.aligned = key.aligned;
     if (blockIdx.x == 0 && threadIdx.x == 0) dbg_stamp(key.own, st->iter, 0);
   }
   spmv_tma_body<D, G, true, GATED>(n_nodes, node_rowptr, node_colidx, values, p, ap, p_own, stages, val_cap, col_cap,

@@ -103,6 +103,7 @@ struct PeerKey {
   int world, rank;
   int lower_tiles, upper_tiles;  // SpMV tiles next to the lower / upper slab face, 0 without that neighbour
   int has_lower, has_upper;
+  int aligned;  // the owned rows of x start and end on 128-byte boundaries
 };
 __device__ __forceinline__ long long peer_tag(const PeerKey& key, long long k) { return (key.epoch << 32) | (k + 1); }
 // Host-side bundle handed down the launch chain: the view in device memory (targets of the publishes

@@ -160,6 +160,7 @@ struct HaloGate {  // a kernel argument (by value): every field is known to the 
   int lower_tiles;             // tiles [0, lower_tiles) gather lower-halo rows
   int upper_tiles;             // tiles [n_tiles - upper_tiles, n_tiles) gather upper-halo rows
   int* error;                  // set to 1 when a neighbour never delivers
+  int aligned;                 // owned / halo borders of x fall on 128-byte boundaries (see below)
 };
 
 // A consumer group is about to start its face tiles: its leader polls the neighbours' tags, then the
@@ -386,7 +387,13 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
 #endif
       if (tile64 < n_tiles) {  // group-uniform
         halo_gate_wait(gate, warp == group * GW && lane == 0, 1 + group, GW * 32);
-        sweep(n_tiles, std::true_type{});
+        // With 128-byte aligned slab borders no line holds both owned and halo rows: halo lines are
+        // first touched here, after the acquire, and may come through L1 like everything else (measured
+        // at N = 8: a rank with two faces lost ~7 us per SpMV to gathering its face tiles through L2).
+        if (gate.aligned)
+          sweep(n_tiles, std::false_type{});
+        else
+          sweep(n_tiles, std::true_type{});
       }
     } else {
       sweep(n_tiles, std::false_type{});

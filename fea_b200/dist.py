@@ -114,15 +114,23 @@ def plan_slab(elements: np.ndarray, cuts: np.ndarray, rank: int) -> SlabPlan:
         ids, g_lo, g_hi = np.empty(0, dtype=np.int64), own_lo, own_hi
     else:
         g_lo, g_hi = min(mn, own_lo), max(mx + 1, own_hi)
+        # Start the local range a few nodes early so that the owned rows begin on a 16-node (= 128-byte for
+        # 3 doubles per node, or any smaller block) boundary of the local vectors: together with cuts at
+        # multiples of 16 (default_cuts) no cache line then holds both owned and halo rows, and the SpMV's
+        # face tiles may gather halo rows through L1 (fea_pcg_solve_p2p).  The extra nodes belong to the
+        # lower neighbour, carry no local element and are never referenced.
+        pad = (-(own_lo - g_lo)) % SLAB_ALIGN_NODES
+        if rank > 0 and g_lo < own_lo and g_lo - pad >= int(cuts[rank - 1]):
+            g_lo -= pad
         if last - first + 1 == count:  # layer-major meshes: a contiguous element range
             ids = np.arange(first, last + 1, dtype=np.int64)
         else:
             ids = np.nonzero(((elements >= own_lo) & (elements < own_hi)).any(axis=1))[0]
     recv_down = recv_up = send_down = send_up = None
-    if g_lo < own_lo:
+    if count and mn < own_lo:
         if rank == 0 or g_lo < cuts[rank - 1]:
             raise ValueError("slab thinner than the mesh bandwidth: halo spans more than one neighbour")
-        recv_down = (rank - 1, g_lo, own_lo)
+        recv_down = (rank - 1, int(mn), own_lo)
     if g_hi > own_hi:
         if rank == world - 1 or g_hi > cuts[rank + 2]:
             raise ValueError("slab thinner than the mesh bandwidth: halo spans more than one neighbour")
@@ -632,10 +640,17 @@ def gather_rows(plan: SlabPlan, cuts, owned: torch.Tensor, group=None, dst: int 
     return None
 
 
+SLAB_ALIGN_NODES = 16  # 16 nodes x 3 doubles = 3 x 128 bytes: slab borders fall on cache-line boundaries
+
+
 def default_cuts(n_nodes: int, world: int) -> np.ndarray:
     """Node-balanced slab cuts (not aligned to mesh layers: 401 layers on 8 ranks would leave one rank
-    with 51 layers against 50, and the slowest rank sets the pace of every iteration)."""
-    return node_cuts(n_nodes, world)
+    with 51 layers against 50, and the slowest rank sets the pace of every iteration), rounded to
+    multiples of 16 nodes so that no cache line of a local vector holds rows of two ranks (plan_slab)."""
+    cuts = node_cuts(n_nodes, world)
+    if n_nodes >= 64 * SLAB_ALIGN_NODES * world:
+        cuts[1:-1] = cuts[1:-1] // SLAB_ALIGN_NODES * SLAB_ALIGN_NODES
+    return cuts
 
 
 def solve_hex8(nodes, elements, constraints, forces, E: float, nu: float, tol: float = 1e-12,

@@ -6,7 +6,7 @@
 Run by tests/test_gpu_parity.py::test_multi_rank_parity (2 ranks when >= 2 GPUs are visible) and by
 hand at N = 2/4/8 (records under profiles/).  Per rank and per variant it checks SURVEY.md §8(e)'s
 bar: owned K rows bit-identical to the single-GPU rows, u within 1e-10 (relative to max|u|), nodal
-forces within 1e-9, same residual history (1e-6) and iteration count (+-2) -- for layer-aligned and
+forces within 1e-9, same residual history (first 100 iterations to 1e-6, decade crossings within 2 %) and iteration count -- for layer-aligned and
 node-balanced cuts, the peer-memory solver with both recurrences, the NCCL driver, and the public
 collective cubebeam.solve (host arrays on rank 0, (None, None) elsewhere).
 """
@@ -71,19 +71,24 @@ def check(label, cuts, comm, algo):
     # residual history: same recurrence, different summation order of the dot products (per rank, then in
     # rank order).  The first 100 iterations must track the single-GPU history to 1e-6.  Later the two
     # runs drift apart like any two roundings of CG on this mesh (the recurrence residual zig-zags over a
-    # decade from one iteration to the next), so the whole history is only held to the same envelope:
-    # running minima within a factor of 10 of each other.
+    # decade from one iteration to the next, and drops by decades within a few iterations), so the rest of
+    # the history is compared through WHEN each decade 1e-1 .. 1e-12 is first reached: within 2 % (+5).
     herr = hlog = None
     if info.history is not None:
         m = min(len(ref_hist), len(info.history))
         k = min(100, m)
         herr = float(np.abs(info.history[:k] / ref_hist[:k] - 1.0).max())
-        hlog = float(np.abs(np.log(np.minimum.accumulate(info.history[:m]) / np.minimum.accumulate(ref_hist[:m]))).max())
+        hlog = 0.0
+        for dec in range(1, 13):
+            ia = np.nonzero(info.history <= 10.0 ** -dec)[0]
+            ib = np.nonzero(ref_hist <= 10.0 ** -dec)[0]
+            if ia.size and ib.size:
+                hlog = max(hlog, abs(int(ia[0]) - int(ib[0])) / max(5.0, 0.02 * int(ib[0])))
     ok = (same_vals and uerr < 1e-10 and ferr < 1e-9 and info.status == 0 and abs(info.iterations - ref_it) <= max(2, ref_it // 100)
-          and (herr is None or (herr < 1e-6 and hlog < np.log(10.0))) and fdist.SOLVER_USED["kind"] == comm)
+          and (herr is None or (herr < 1e-6 and hlog <= 1.0)) and fdist.SOLVER_USED["kind"] == comm)
     rec = dict(variant=label, rank=rank, owned_nodes=plan.n_owned, k_rows_bit_identical=same_vals, u_err=uerr,
                f_err=ferr, iterations=info.iterations, iterations_1gpu=ref_it, history_err_first_100=herr,
-               history_envelope_max_log_ratio=hlog,
+               history_decade_crossing_shift=hlog,
                rel_residual=info.rel_residual, status=info.status, solver=fdist.SOLVER_USED["kind"], ok=bool(ok))
     records.append(rec)
 
