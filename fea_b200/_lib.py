@@ -110,6 +110,12 @@ PROTOTYPES = {
     "fea_pcg_multi_workspace": (c_size_t, [c_int64, c_int32]),
     "fea_pcg_solve_multi": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, c_int32, c_double, c_int32, P, c_size_t,
                                       P, ctypes.POINTER(PcgResult), P]),
+    "fea_pcg_multi_layout": (c_int32, [c_int32, P]),
+    "fea_pcg_multi_init": (c_int32, [c_int64, c_int32, P, P, P, P, c_double, c_int32, P, c_size_t, P]),
+    "fea_pcg_multi_activate": (c_int32, [c_int64, c_int32, P, P]),
+    "fea_pcg_multi_step_spmm": (c_int32, [c_int64, c_int32, P, P, P, P, c_int64, c_int32, P, P]),
+    "fea_pcg_multi_step_update": (c_int32, [c_int64, c_int32, P, P, P, P, P]),
+    "fea_pcg_multi_step_direction": (c_int32, [c_int64, c_int32, P, P, P, P]),
     "fea_truss_member_forces": (c_int32, [P, P, P, c_int64, c_int64, P, P, P, P, c_int32, P]),
     "fea_truss_relax": (c_int32, [P, P, P, c_int64, c_int64, P, P, P, P, c_int64, c_double, c_int32, P, P, P, c_int32,
                                   P]),

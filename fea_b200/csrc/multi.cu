@@ -186,7 +186,7 @@ template <int D, int CPL, int G, int U, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 multi_spmm_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
                   const double* __restrict__ values, const double* __restrict__ P, double* __restrict__ AP, int R,
-                  MultiWork w) {
+                  MultiWork w, const double* __restrict__ Pown) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ double s_cols[kMaxRhs];
   __shared__ double s_red[1][8][32 * CPL + 1];
@@ -200,7 +200,7 @@ multi_spmm_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, cons
 #pragma unroll
     for (int j = 0; j < CPL; ++j) dot[0][j] = 0.0;
     spmm_sweep<D, CPL, G, U, true>(n_nodes, node_rowptr, node_colidx, values, P, AP, R, col0, col0 < R, lane, warp, sm,
-                                   dot);
+                                   dot, Pown);
     fold_columns<CPL, 1>(dot, col0, R, s_cols, s_red);
   }
   if (publish_columns(w.partials, s_cols, 1, R, &w.st->counter[0])) {
@@ -385,25 +385,48 @@ multi_direction_kernel(int64_t n, int R, const double* __restrict__ dinv, const 
 
 template <int D, int CPL, int G, int U, int MINB>
 static int launch_multi_spmm_variant(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
-                                     const double* P, double* AP, int R, const MultiWork& w, cudaStream_t stream) {
+                                     const double* P, double* AP, int R, const MultiWork& w, cudaStream_t stream,
+                                     const double* Pown = nullptr) {
   constexpr size_t smem = sizeof(SpmmGroupSmem<D, G>) * kSpmmWarps;
   // per call: the attribute is per device, and a process may drive several (a few hundred ns on the host)
   FEA_TRY(check(cudaFuncSetAttribute(multi_spmm_kernel<D, CPL, G, U, MINB>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   const unsigned blocks = (unsigned)std::max<int64_t>(
       1, std::min<int64_t>(ceil_div(ceil_div(n_nodes, G), kSpmmWarps), std::min(148 * 2 * MINB, kMultiBlocks)));
-  multi_spmm_kernel<D, CPL, G, U, MINB><<<blocks, dim3(32, 8), smem, stream>>>(n_nodes, rp, ci, values, P, AP, R, w);
+  multi_spmm_kernel<D, CPL, G, U, MINB><<<blocks, dim3(32, 8), smem, stream>>>(n_nodes, rp, ci, values, P, AP, R, w,
+                                                                               Pown);
   return FEA_OK;
 }
 
 template <int D>
 static int launch_multi_spmm(int64_t n_nodes, const int32_t* rp, const int32_t* ci, const double* values,
-                             const double* P, double* AP, int R, bool vec, const MultiWork& w, cudaStream_t stream) {
-  if (!vec) return launch_multi_spmm_variant<D, 1, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream);
+                             const double* P, double* AP, int R, bool vec, const MultiWork& w, cudaStream_t stream,
+                             const double* Pown = nullptr) {
+  if (!vec) return launch_multi_spmm_variant<D, 1, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
   switch (spmm_variant()) {
-    case 1: return launch_multi_spmm_variant<D, 2, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream);
-    case 2: return launch_multi_spmm_variant<D, 2, 1, 3, 3>(n_nodes, rp, ci, values, P, AP, R, w, stream);
-    default: return launch_multi_spmm_variant<D, 2, 2, 3, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream);
+    case 1: return launch_multi_spmm_variant<D, 2, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
+    case 2: return launch_multi_spmm_variant<D, 2, 1, 3, 3>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
+    default: return launch_multi_spmm_variant<D, 2, 2, 3, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
+  }
+}
+
+// Multi-GPU driver: after the world sums of (r.z, ||b||^2) have replaced the local ones, derive the
+// per-column activity flags and the done flag from the WORLD norms (the init kernel did it from local
+// ones: a rank whose slab carries no load of some column would otherwise switch that column off).
+__global__ void multi_activate_kernel(MultiWork w) {
+  const int R = w.st->n_rhs;
+  int act = 0;
+  for (int col = threadIdx.x; col < R; col += blockDim.x) {
+    const int a = w.bnorm2[col] > 0.0 ? 1 : 0;
+    w.active[col] = a;
+    w.rr[col] = w.bnorm2[col];
+    w.rz_new[col] = 0.0;
+    act += a;
+  }
+  act = __syncthreads_count(act);
+  if (threadIdx.x == 0) {
+    w.st->n_active = act;
+    w.st->done = act == 0;
   }
 }
 
@@ -517,4 +540,101 @@ extern "C" int fea_pcg_solve_multi(int64_t n_nodes, int32_t d, const int32_t* no
   cudaEventDestroy(ev[0]);
   cudaEventDestroy(ev[1]);
   return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Step-level entry points of the batched solver, for the multi-GPU driver (fea_b200/dist.py:
+// distributed_pcg_multi): the same kernels as fea_pcg_solve_multi on one rank's slab, with the caller
+// all-reducing the per-column scalars in between -- exactly the places where the single-GPU solver's
+// last blocks finish their column sums:
+//   init                 -> all-reduce scalars[0 .. 2R)  (r.z, ||b||^2)        -> activate
+//   step_spmm            -> all-reduce scalars[4R .. 5R) (p.Ap)
+//   step_update          -> all-reduce scalars[2R .. 4R) (r.z new, r.r)
+//   step_direction          (convergence bookkeeping on the world sums: identical on every rank)
+// P is the caller's halo-extended (n_local_dof, R) array; the solver's other vectors live in `work`.
+static bool multi_vec_ok(int R, const void* a, const void* b, const void* c) {
+  return spmm_can_vectorise(R, a, b) && (reinterpret_cast<uintptr_t>(c) & 15u) == 0;
+}
+
+extern "C" int fea_pcg_multi_layout(int32_t n_rhs, int64_t* offsets_host) {
+  // byte offsets inside the workspace: [0] state (64 B: iter, done, status, max_iter, n_active, n_rhs),
+  // [1] the 5R per-column doubles rz | bnorm2 | rz_new | rr | pap, [2] active (R int32), [3] iters (R int32)
+  if (!offsets_host || n_rhs < 1) return FEA_ERR_INVALID;
+  offsets_host[0] = 0;
+  offsets_host[1] = 256;
+  offsets_host[2] = 256 + (int64_t)align256(sizeof(double) * 5 * n_rhs);
+  offsets_host[3] = offsets_host[2] + (int64_t)sizeof(int32_t) * n_rhs;
+  return FEA_OK;
+}
+
+extern "C" int fea_pcg_multi_init(int64_t n_dof, int32_t n_rhs, const double* B, const double* dinv, double* X,
+                                  double* P_own, double tol, int32_t max_iter, void* work, size_t work_bytes,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!B || !dinv || !X || !P_own || !work || n_dof <= 0 || n_rhs < 1 || n_rhs > kMaxRhs || max_iter < 1)
+    return FEA_ERR_INVALID;
+  if (work_bytes < multi_bytes(n_dof, n_rhs)) return FEA_ERR_WORKSPACE;
+  MultiWork w = carve_multi(work, n_dof, n_rhs);
+  const unsigned vb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_dof, 8 * 8), kMultiBlocks));
+  FEA_TRY(check(cudaMemsetAsync(w.st, 0, 256, stream)));
+  if (multi_vec_ok(n_rhs, B, X, P_own))
+    multi_init_kernel<2><<<vb, dim3(32, 8), 0, stream>>>(n_dof, n_rhs, B, dinv, X, w.Rv, P_own, tol, max_iter, w);
+  else
+    multi_init_kernel<1><<<vb, dim3(32, 8), 0, stream>>>(n_dof, n_rhs, B, dinv, X, w.Rv, P_own, tol, max_iter, w);
+  return check_launch();
+}
+
+extern "C" int fea_pcg_multi_activate(int64_t n_dof, int32_t n_rhs, void* work, void* stream_) {
+  if (!work || n_dof <= 0 || n_rhs < 1 || n_rhs > kMaxRhs) return FEA_ERR_INVALID;
+  multi_activate_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(carve_multi(work, n_dof, n_rhs));
+  return check_launch();
+}
+
+extern "C" int fea_pcg_multi_step_spmm(int64_t n_owned_nodes, int32_t d, const int32_t* node_rowptr_owned,
+                                       const int32_t* node_colidx, const double* values, const double* P_ext,
+                                       int64_t p_row_offset, int32_t n_rhs, void* work, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!node_rowptr_owned || !node_colidx || !values || !P_ext || !work || n_owned_nodes <= 0 || n_rhs < 1 ||
+      n_rhs > kMaxRhs || p_row_offset < 0)
+    return FEA_ERR_INVALID;
+  const int64_t n = n_owned_nodes * d;
+  MultiWork w = carve_multi(work, n, n_rhs);
+  const double* Pown = P_ext + (size_t)p_row_offset * d * n_rhs;
+  const bool vec = multi_vec_ok(n_rhs, P_ext, w.AP, Pown);
+  int rc;
+  switch (d) {
+    case 1: rc = launch_multi_spmm<1>(n_owned_nodes, node_rowptr_owned, node_colidx, values, P_ext, w.AP, n_rhs, vec, w, stream, Pown); break;
+    case 2: rc = launch_multi_spmm<2>(n_owned_nodes, node_rowptr_owned, node_colidx, values, P_ext, w.AP, n_rhs, vec, w, stream, Pown); break;
+    case 3: rc = launch_multi_spmm<3>(n_owned_nodes, node_rowptr_owned, node_colidx, values, P_ext, w.AP, n_rhs, vec, w, stream, Pown); break;
+    default: return FEA_ERR_INVALID;
+  }
+  FEA_TRY(rc);
+  return check_launch();
+}
+
+extern "C" int fea_pcg_multi_step_update(int64_t n_dof, int32_t n_rhs, const double* dinv, const double* P_own,
+                                         double* X, void* work, void* stream_) {
+  if (!dinv || !P_own || !X || !work || n_dof <= 0 || n_rhs < 1 || n_rhs > kMaxRhs) return FEA_ERR_INVALID;
+  MultiWork w = carve_multi(work, n_dof, n_rhs);
+  const unsigned vb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_dof, 8 * 8), kMultiBlocks));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (multi_vec_ok(n_rhs, P_own, X, w.AP))
+    multi_update_kernel<2><<<vb, dim3(32, 8), 0, stream>>>(n_dof, n_rhs, dinv, P_own, w.AP, X, w.Rv, w);
+  else
+    multi_update_kernel<1><<<vb, dim3(32, 8), 0, stream>>>(n_dof, n_rhs, dinv, P_own, w.AP, X, w.Rv, w);
+  return check_launch();
+}
+
+extern "C" int fea_pcg_multi_step_direction(int64_t n_dof, int32_t n_rhs, const double* dinv, double* P_own,
+                                            void* work, void* stream_) {
+  if (!dinv || !P_own || !work || n_dof <= 0 || n_rhs < 1 || n_rhs > kMaxRhs) return FEA_ERR_INVALID;
+  MultiWork w = carve_multi(work, n_dof, n_rhs);
+  const unsigned vb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_dof, 8 * 8), kMultiBlocks));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (multi_vec_ok(n_rhs, P_own, w.Rv, w.AP))
+    multi_direction_kernel<2><<<vb, dim3(32, 8), 0, stream>>>(n_dof, n_rhs, dinv, w.Rv, P_own, w);
+  else
+    multi_direction_kernel<1><<<vb, dim3(32, 8), 0, stream>>>(n_dof, n_rhs, dinv, w.Rv, P_own, w);
+  return check_launch();
 }

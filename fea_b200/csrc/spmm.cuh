@@ -317,7 +317,11 @@ __device__ __forceinline__ void spmm_sweep(int64_t n_nodes, const int32_t* __res
                                            const int32_t* __restrict__ node_colidx,
                                            const double* __restrict__ values, const double* __restrict__ X,
                                            double* __restrict__ Y, int R, int col0, bool active, int lane, int warp,
-                                           SpmmGroupSmem<D, G>& sm, double (&dot)[1][CPL]) {
+                                           SpmmGroupSmem<D, G>& sm, double (&dot)[1][CPL],
+                                           const double* __restrict__ Xown = nullptr) {
+  // Xown: the rows of X that belong to the output rows (X + row offset of a slab's owned rows); X itself
+  // when null.  Only the fused dot reads it.
+  if (Xown == nullptr) Xown = X;
   auto finish = [&](int64_t node, const double (&acc)[D][CPL]) {
     if (!active) return;
 #pragma unroll
@@ -326,7 +330,7 @@ __device__ __forceinline__ void spmm_sweep(int64_t n_nodes, const int32_t* __res
       ColVec<CPL>::store(Y + idx, acc[a]);
       if (DOT) {
         double own[CPL];
-        ColVec<CPL>::load(X + idx, own);
+        ColVec<CPL>::load(Xown + idx, own);
 #pragma unroll
         for (int j = 0; j < CPL; ++j) dot[0][j] = fma(acc[a][j], own[j], dot[0][j]);
       }

@@ -643,6 +643,116 @@ def gather_rows(plan: SlabPlan, cuts, owned: torch.Tensor, group=None, dst: int 
 SLAB_ALIGN_NODES = 16  # 16 nodes x 3 doubles = 3 x 128 bytes: slab borders fall on cache-line boundaries
 
 
+# ------------------------------------------------------------------------------------------------
+# multi-RHS (BASELINE config 5) on slabs: the batched solver's step kernels + NCCL in between
+# ------------------------------------------------------------------------------------------------
+def distributed_pcg_multi(K, plan: SlabPlan, B_owned: torch.Tensor, dinv_owned: torch.Tensor, tol: float = 1e-12,
+                          max_iter: int = 100000, chunk: int = 16, group=None):
+    """Batched Jacobi-PCG (one recurrence per column, as fea_pcg_solve_multi) over all ranks.
+    B_owned (n_owned_dof, R).  Per iteration: halo exchange of the (rows, R) search directions with the two
+    slab neighbours (grouped NCCL send / recv), SpMM on the owned rows with the per-column p.Ap fused,
+    all-reduce of R sums, update, all-reduce of 2R sums, direction.  Returns (X_owned, DistInfo) with
+    info.history = iterations per column."""
+    import ctypes
+
+    from . import core
+
+    lib = _lib.load()
+    d = K.dof_per_node
+    n_own, R = plan.n_owned * d, int(B_owned.shape[1])
+    dev = B_owned.device
+    B_owned = B_owned.contiguous()
+    X = torch.empty_like(B_owned)
+    P_ext = torch.zeros((plan.n_local * d, R), dtype=torch.float64, device=dev)
+    P_own = P_ext[plan.offset * d:plan.offset * d + n_own]
+    ws_bytes = lib.fea_pcg_multi_workspace(n_own, R)
+    work = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    off = (ctypes.c_int64 * 4)()
+    _lib.check(lib.fea_pcg_multi_layout(R, ctypes.addressof(off)), "fea_pcg_multi_layout")
+    state = work[off[0]:off[0] + 64].view(torch.int32)
+    scal = work[off[1]:off[1] + 8 * 5 * R].view(torch.float64)
+    iters = work[off[3]:off[3] + 4 * R].view(torch.int32)
+    pt = K.pattern
+    rowptr_owned = pt.node_rowptr[plan.offset:]
+    halo = HaloExchange(plan, d, group)
+    multi = plan.world > 1
+    s = core._stream
+    _lib.check(lib.fea_pcg_multi_init(n_own, R, B_owned.data_ptr(), dinv_owned.data_ptr(), X.data_ptr(),
+                                      P_own.data_ptr(), float(tol), int(max_iter), work.data_ptr(), ws_bytes, s()),
+               "fea_pcg_multi_init")
+    if multi:
+        dist.all_reduce(scal[:2 * R], group=group)
+    _lib.check(lib.fea_pcg_multi_activate(n_own, R, work.data_ptr(), s()), "fea_pcg_multi_activate")
+    done_iter, finished = 0, False
+    while not finished:
+        todo = min(chunk, max_iter - done_iter)
+        for _ in range(todo):
+            halo(P_ext)
+            _lib.check(lib.fea_pcg_multi_step_spmm(plan.n_owned, d, rowptr_owned.data_ptr(), pt.node_colidx.data_ptr(),
+                                                   K.values.data_ptr(), P_ext.data_ptr(), plan.offset, R,
+                                                   work.data_ptr(), s()), "fea_pcg_multi_step_spmm")
+            if multi:
+                dist.all_reduce(scal[4 * R:5 * R], group=group)
+            _lib.check(lib.fea_pcg_multi_step_update(n_own, R, dinv_owned.data_ptr(), P_own.data_ptr(), X.data_ptr(),
+                                                     work.data_ptr(), s()), "fea_pcg_multi_step_update")
+            if multi:
+                dist.all_reduce(scal[2 * R:4 * R], group=group)
+            _lib.check(lib.fea_pcg_multi_step_direction(n_own, R, dinv_owned.data_ptr(), P_own.data_ptr(),
+                                                        work.data_ptr(), s()), "fea_pcg_multi_step_direction")
+        done_iter += todo
+        st = state.cpu()  # one synchronisation per chunk; the decisions are identical on every rank
+        finished = bool(int(st[1]) != 0) or done_iter >= max_iter
+    st = state.cpu()
+    sc = scal.cpu().numpy()
+    bn2, rr = sc[R:2 * R], sc[3 * R:4 * R]
+    worst = float(np.sqrt((rr[bn2 > 0] / bn2[bn2 > 0]).max())) if (bn2 > 0).any() else 0.0
+    status = int(st[2])
+    if int(st[1]) == 0 and status == _lib.FEA_OK:
+        status = _lib.FEA_ERR_MAXITER
+    return X, DistInfo(int(st[0]), worst, status, float(np.sqrt(bn2.max())), iters.cpu().numpy().astype(np.int64))
+
+
+def solve_truss_multi(nodes, members, k, constraints, loads, tol: float = 1e-12, max_iter: int | None = None,
+                      group=None, cuts=None, gather: bool = True):
+    """Linear truss K U = F for R load cases (BASELINE config 5) on every GPU of the process group:
+    COLLECTIVE, every rank passes the same global host arrays (loads (3N, R)).  The lattice generator
+    numbers nodes z-major, so a contiguous node range is a slab.  Returns
+    (U (3N, R) host array on rank 0 / None elsewhere [device shards if not `gather`], DistInfo)."""
+    from . import core
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nodes = np.asarray(nodes, dtype=np.float64)
+    members = np.asarray(members).reshape(-1, 2)
+    n_nodes = nodes.shape[0]
+    if cuts is None:
+        cuts = default_cuts(n_nodes, world)
+    plan = plan_slab(members, cuts, rank)
+    g_lo, g_hi = plan.g_lo, plan.g_hi
+    ids = plan.element_ids
+    nodes_d = core.to_device(np.ascontiguousarray(nodes[g_lo:g_hi]), torch.float64)
+    members_d = core.to_device(np.ascontiguousarray(members[ids] - g_lo), torch.int32)
+    k_d = core.to_device(np.ascontiguousarray(np.asarray(k, dtype=np.float64)[ids]), torch.float64)
+    fixed = core._fixed_mask(np.ascontiguousarray(np.asarray(constraints)[g_lo:g_hi]), 3 * plan.n_local)
+    K = core.assemble_truss(nodes_d, members_d, k_d, fixed=fixed)
+    lo, hi = 3 * plan.offset, 3 * (plan.offset + plan.n_owned)
+    dinv_owned = K.dinv[lo:hi].contiguous()
+    loads = np.asarray(loads, dtype=np.float64)
+    B_owned = core.to_device(np.ascontiguousarray(loads[3 * plan.own_lo:3 * plan.own_hi]), torch.float64)
+    if max_iter is None:
+        max_iter = min(10 * 3 * n_nodes, 2**31 - 1)
+    X, info = distributed_pcg_multi(K, plan, B_owned, dinv_owned, tol=tol, max_iter=max_iter, group=group)
+    if info.status != _lib.FEA_OK:
+        _lib.raise_for_status(np.array([info.status, 0x7FFFFFFF - info.iterations]))
+    if not gather:
+        return X, info
+    R = X.shape[1]
+    full = gather_rows(plan, cuts, X.reshape(1, plan.n_owned, 3 * R), group=group)
+    out = None
+    if full is not None:
+        out = full.reshape(n_nodes * 3, R).cpu().numpy()
+    return out, info
+
+
 def default_cuts(n_nodes: int, world: int) -> np.ndarray:
     """Node-balanced slab cuts (not aligned to mesh layers: 401 layers on 8 ranks would leave one rank
     with 51 layers against 50, and the slowest rank sets the pace of every iteration), rounded to

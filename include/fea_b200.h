@@ -290,6 +290,30 @@ int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t dof_per_node, const int32_t
                       void* work, size_t work_bytes, double* history, const fea_peer_comm* comm,
                       fea_pcg_result* result_host, void* stream);
 
+/* Step-level entry points of the batched solver, for a multi-GPU driver (fea_b200/dist.py:
+ * distributed_pcg_multi): the kernels of fea_pcg_solve_multi on one rank's slab of rows; the caller sums
+ * the per-column scalars over the ranks in between (any all-reduce; NCCL in dist.py):
+ *   fea_pcg_multi_init             -> sum scalars[0 .. 2R) (r.z, ||b||^2), then fea_pcg_multi_activate
+ *   fea_pcg_multi_step_spmm        -> sum scalars[4R .. 5R) (p.Ap); P_ext is the halo-extended
+ *                                     (n_local_dof, R) array, owned rows start at node p_row_offset
+ *   fea_pcg_multi_step_update      -> sum scalars[2R .. 4R) (new r.z, r.r)
+ *   fea_pcg_multi_step_direction      convergence bookkeeping on the world sums (identical everywhere)
+ * `work`: fea_pcg_multi_workspace(n_owned_dof, R) bytes.  fea_pcg_multi_layout gives the byte offsets in it
+ * of {state (int32: iter, done, status, max_iter, n_active, n_rhs), the 5R doubles rz | bnorm2 | rz_new |
+ * rr | pap, active (R int32), iterations per column (R int32)}. */
+int fea_pcg_multi_layout(int32_t n_rhs, int64_t* offsets_host);
+int fea_pcg_multi_init(int64_t n_dof, int32_t n_rhs, const double* B, const double* dinv, double* X,
+                       double* P_own, double tol, int32_t max_iter, void* work, size_t work_bytes,
+                       void* stream);
+int fea_pcg_multi_activate(int64_t n_dof, int32_t n_rhs, void* work, void* stream);
+int fea_pcg_multi_step_spmm(int64_t n_owned_nodes, int32_t dof_per_node, const int32_t* node_rowptr_owned,
+                            const int32_t* node_colidx, const double* values, const double* P_ext,
+                            int64_t p_row_offset, int32_t n_rhs, void* work, void* stream);
+int fea_pcg_multi_step_update(int64_t n_dof, int32_t n_rhs, const double* dinv, const double* P_own,
+                              double* X, void* work, void* stream);
+int fea_pcg_multi_step_direction(int64_t n_dof, int32_t n_rhs, const double* dinv, double* P_own,
+                                 void* work, void* stream);
+
 /* Direct solve of a CHAIN mesh (every node couples to its two neighbours only: the Euler-Bernoulli beam
  * of euler_bernoulli.py:42-73, dof_per_node = 2; or 1): block-tridiagonal parallel cyclic reduction,
  * ceil(log2 n) steps, replaces `np.linalg.solve` (euler_bernoulli.py:69) where Jacobi-PCG cannot

