@@ -85,7 +85,6 @@ PROTOTYPES = {
                                     P, P, P, P]),
     "fea_assemble_beam": (c_int32, [P, P, P, c_int64, c_int64, P, P, P, P, P, c_int32, P, P, P]),
     "fea_assemble_truss": (c_int32, [P, P, P, c_int64, c_int64, P, P, P, P, P, c_int32, P, P, P, P]),
-    "fea_assemble_hex8_scatter": (c_int32, [P, P, c_int64, c_double, c_double, P, P, P, P, P]),
     "fea_jacobi_dinv": (c_int32, [c_int64, c_int32, P, P, P, P, P, P]),
     "fea_spmv": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, P]),
     "fea_spmm": (c_int32, [c_int64, c_int32, P, P, P, P, P, c_int32, P]),

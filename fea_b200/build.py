@@ -45,18 +45,27 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+CHECKED_LIB_PATH = os.path.join(CSRC, "libfea_b200_checked.so")
+
+
+def build_library(force: bool = False, verbose: bool = False, checked: bool = False) -> str:
+    """checked=True: -DFEA_CHECKED (device-side assertions, csrc/common.cuh) into libfea_b200_checked.so,
+    objects under csrc/checked/."""
     nvcc = find_nvcc()
+    lib_path = CHECKED_LIB_PATH if checked else LIB_PATH
+    obj_dir = os.path.join(CSRC, "checked") if checked else CSRC
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = NVCC_FLAGS + (["-DFEA_CHECKED"] if checked else [])
     sources = [s for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
     headers = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     common_deps = [os.path.join(CSRC, h) for h in headers] + [os.path.join(INCLUDE, "fea_b200.h"), __file__]
     objs, jobs = [], []
     for src in sources:
         src_path = os.path.join(CSRC, src)
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src_path] + common_deps):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", src_path, "-o", obj]
+            cmd = [nvcc, *flags, "-c", src_path, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
@@ -72,12 +81,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             for log in pool.map(run, jobs):
                 if verbose and log:
                     print(log, file=sys.stderr)
-    if jobs or force or _stale(LIB_PATH, objs):
-        run([nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
+    if jobs or force or _stale(lib_path, objs):
+        run([nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static",
              "-lpthread", "-ldl", "-lrt"])
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv, checked="--checked" in sys.argv)
     print(path)

@@ -40,7 +40,6 @@ __device__ __forceinline__ double eliminate(double v, const uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------
 constexpr int kAsmWarps = 4;
 
-template <bool FACTORED>
 __global__ void __launch_bounds__(kAsmWarps * 32)
 assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ elements, int64_t n_nodes,
                      Hex8Material mat, const int32_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e,
@@ -91,8 +90,9 @@ assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict
       int slot = 0;
       if (active) {  // phase B
         const int b = lane & 7;
-        hex8_block<FACTORED>(grad, detj, t, a_own, b, mat, blk);
+        hex8_block(grad, detj, t, a_own, b, mat, blk);
         slot = find_slot(cols, cnt, elements[(int64_t)e * 8 + b]);
+        FEA_ASSERT(slot >= 0 && slot < cnt && cols[slot] == elements[(int64_t)e * 8 + b]);
       }
       // phase C: element order; inside one element the 8 column nodes are distinct
 #pragma unroll
@@ -239,56 +239,6 @@ assemble_slot_owner_kernel(Op op, const int32_t* __restrict__ elements, int64_t 
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Scatter-add alternative for hex8 (the textbook GPU assembly): warp per 4 elements, every lane
-// (t, b) pushes the 8 blocks K_ab of its element with FP64 atomics.  Kept for comparison.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kAsmWarps * 32)
-assemble_hex8_scatter_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ elements, int64_t n_elem,
-                             Hex8Material mat, const int32_t* __restrict__ node_rowptr,
-                             const int32_t* __restrict__ node_colidx, double* __restrict__ values,
-                             int32_t* status) {
-  __shared__ double s_tab[kShapeTable];
-  __shared__ double s_grad[kAsmWarps][kGradDoubles];
-  __shared__ double s_detj[kAsmWarps][32];
-  hex8_fill_shape_table(s_tab);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* grad = s_grad[warp];
-  double* detj = s_detj[warp];
-  const int64_t n_groups = (n_elem + 3) / 4;
-  for (int64_t g = (int64_t)blockIdx.x * kAsmWarps + warp; g < n_groups; g += (int64_t)gridDim.x * kAsmWarps) {
-    const int t = lane >> 3;
-    const int64_t e = g * 4 + t;
-    if (e < n_elem) {
-      const int gp = lane & 7;
-      const double det = hex8_geometry(nodes, elements + e * 8, s_tab, gp, t, grad);
-      detj[gp * 4 + t] = det;
-      if (!(det > 0.0)) raise_status(status, FEA_ERR_JACOBIAN, (int)e);
-    }
-    __syncwarp();
-    if (e < n_elem) {
-      const int b = lane & 7;
-      const int col = elements[e * 8 + b];
-#pragma unroll 1
-      for (int a = 0; a < 8; ++a) {
-        const int row_node = elements[e * 8 + a];
-        const int lo = node_rowptr[row_node];
-        const int cnt = node_rowptr[row_node + 1] - lo;
-        const int slot = find_slot(node_colidx + lo, cnt, col);
-        double blk[3][3];
-        hex8_block(grad, detj, t, a, b, mat, blk);
-        double* dst = values + 9 * (int64_t)lo + 3 * slot;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) atomicAdd(dst + (int64_t)r * 3 * cnt + c, blk[r][c]);
-      }
-    }
-    __syncwarp();
-  }
-}
-
 __global__ void __launch_bounds__(256)
 jacobi_dinv_kernel(int64_t n_nodes, int d, const int32_t* __restrict__ node_rowptr,
                    const int32_t* __restrict__ node_colidx, const double* __restrict__ values,
@@ -327,22 +277,13 @@ extern "C" int fea_assemble_hex8(const double* nodes, const int32_t* elements, i
   const int per_warp = kGradDoubles + 32 + 9 * maxc + (maxc + 1) / 2;
   const size_t smem = sizeof(double) * (kShapeTable + (size_t)kAsmWarps * per_warp);
   if (smem > 200 * 1024) return FEA_ERR_INVALID;  // valence too high for the on-chip accumulator
-  const bool legacy = hex8_legacy_block();
   if (smem > 48 * 1024) {
-    FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem)));
-    FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem)));
+    FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   }
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, kAsmWarps), 148LL * 64);
-  if (legacy)
-    assemble_hex8_kernel<false><<<blocks, kAsmWarps * 32, smem, stream>>>(
-        nodes, elements, n_nodes, hex8_material(E, nu), n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed, mode,
-        values, dinv, status);
-  else
-    assemble_hex8_kernel<true><<<blocks, kAsmWarps * 32, smem, stream>>>(
-        nodes, elements, n_nodes, hex8_material(E, nu), n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed, mode,
-        values, dinv, status);
+  assemble_hex8_kernel<<<blocks, kAsmWarps * 32, smem, stream>>>(nodes, elements, n_nodes, hex8_material(E, nu), n2e_ptr,
+                                                                 n2e, node_rowptr, node_colidx, maxc, fixed, mode, values,
+                                                                 dinv, status);
   return check_launch();
 }
 
@@ -379,19 +320,6 @@ extern "C" int fea_assemble_truss(const double* nodes, const int32_t* members, c
   TrussOp op{nodes, members, k};
   return launch_slot_owner(op, members, n_nodes, n2e_ptr, n2e, node_rowptr, node_colidx, fixed, mode, values, dinv,
                            status, static_cast<cudaStream_t>(stream_));
-}
-
-extern "C" int fea_assemble_hex8_scatter(const double* nodes, const int32_t* elements, int64_t n_elem, double E,
-                                         double nu, const int32_t* node_rowptr, const int32_t* node_colidx,
-                                         double* values, int32_t* status, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!nodes || !elements || !node_rowptr || !node_colidx || !values || n_elem < 0) return FEA_ERR_INVALID;
-  if (n_elem == 0) return FEA_OK;
-  const int64_t groups = ceil_div(n_elem, 4);
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(groups, kAsmWarps), 148LL * 16);
-  assemble_hex8_scatter_kernel<<<blocks, kAsmWarps * 32, 0, stream>>>(nodes, elements, n_elem, hex8_material(E, nu),
-                                                                      node_rowptr, node_colidx, values, status);
-  return check_launch();
 }
 
 extern "C" int fea_jacobi_dinv(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,

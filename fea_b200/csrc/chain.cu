@@ -143,6 +143,7 @@ __global__ void chain_extract_kernel(int64_t n, const int32_t* __restrict__ rp, 
 #pragma unroll
   for (int q = 0; q < D * D; ++q) row.a[q] = row.b[q] = row.c[q] = make_real<Real>(0.0);
   const int lo = rp[i], cnt = rp[i + 1] - lo;
+  FEA_ASSERT(cnt >= 0 && cnt <= 3);
   bool has_diag = false;
   for (int k = 0; k < cnt; ++k) {
     const int64_t j = ci[lo + k];

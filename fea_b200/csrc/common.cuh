@@ -7,6 +7,19 @@
 
 #include "fea_b200.h"
 
+// Checked build (python -m fea_b200.build --checked -> libfea_b200_checked.so): device-side assertions on
+// every index the kernels derive from the pattern -- staging offsets and capacities of the bulk-copy ring,
+// slot searches of the assembly, partial-sum slots, peer-slot indices.  compute-sanitizer is closed on
+// the GPU pool this was developed on, so this is the memcheck of the project: tests/test_gpu_parity.py::
+// test_checked_build runs tools/sanitize.py (every kernel family, small cases, results compared with the
+// oracle) against it; a violated assertion prints file:line and fails the CUDA context.
+#ifdef FEA_CHECKED
+#include <cassert>
+#define FEA_ASSERT(cond) assert(cond)
+#else
+#define FEA_ASSERT(cond) ((void)0)
+#endif
+
 namespace fea {
 
 constexpr int kWarp = 32;

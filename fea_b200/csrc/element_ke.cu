@@ -14,7 +14,6 @@ namespace fea {
 //   phase B: lane = (t, b): the eight 3x3 blocks K_ab, a = 0..7, written to ke[e][3a+r][3b+c].
 constexpr int kKeWarps = 4;
 
-template <bool FACTORED>
 __global__ void __launch_bounds__(kKeWarps * 32) ke_hex8_kernel(const double* __restrict__ nodes,
                                                                 const int32_t* __restrict__ elements,
                                                                 int64_t n_elem, Hex8Material mat,
@@ -52,7 +51,7 @@ __global__ void __launch_bounds__(kKeWarps * 32) ke_hex8_kernel(const double* __
       for (int a = 0; a < 8; ++a) {
         if (e < n_elem) {
           double blk[3][3];
-          hex8_block<FACTORED>(grad, detj, t, a, b, mat, blk);
+          hex8_block(grad, detj, t, a, b, mat, blk);
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -121,12 +120,7 @@ extern "C" int fea_ke_hex8(const double* nodes, const int32_t* elements, int64_t
   if (n_elem == 0) return FEA_OK;
   const int64_t groups = ceil_div(n_elem, 4);
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(groups, kKeWarps), 148LL * 16);
-  if (hex8_legacy_block())
-    ke_hex8_kernel<false><<<blocks, kKeWarps * 32, 0, stream>>>(nodes, elements, n_elem, hex8_material(E, nu), ke,
-                                                                  status);
-  else
-    ke_hex8_kernel<true><<<blocks, kKeWarps * 32, 0, stream>>>(nodes, elements, n_elem, hex8_material(E, nu), ke,
-                                                                 status);
+  ke_hex8_kernel<<<blocks, kKeWarps * 32, 0, stream>>>(nodes, elements, n_elem, hex8_material(E, nu), ke, status);
   return check_launch();
 }
 

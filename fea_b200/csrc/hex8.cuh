@@ -116,36 +116,10 @@ __device__ __forceinline__ double hex8_geometry(const double* __restrict__ nodes
 // 3x3 block K_ab of one element (slot t of the staging area).  With S[r][c] = sum_gp detJ ga_r gb_c
 // (Gauss points in the reference's order, weights 1) the material constants factor out of the
 // quadrature:  K_ab[r][r] = C11 S_rr + C44 (S_ss + S_tt),  K_ab[r][c] = C12 S_rc + C44 S_cr,
-// 12 flops per Gauss point instead of 45 for the multiplied-out form.
-template <bool FACTORED = true>
+// 12 flops per Gauss point instead of 45 for the multiplied-out form (round 1 measured both: 5 % apart,
+// the kernel is not flop-bound; the multiplied-out variant is gone).
 __device__ __forceinline__ void hex8_block(const double* __restrict__ grad, const double* __restrict__ detj, int t,
                                            int a, int b, const Hex8Material& m, double blk[3][3]) {
-  if constexpr (!FACTORED) {  // multiplied-out form, 45 flops per Gauss point (kept for A/B timing: FEA_HEX8_LEGACY=1)
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) blk[r][c] = 0.0;
-#pragma unroll
-    for (int gp = 0; gp < 8; ++gp) {
-      const double w = detj[gp * 4 + t];
-      double ga[3], gb[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        ga[r] = grad[(r * 8 + gp) * kGradStride + t * 8 + a];
-        gb[r] = grad[(r * 8 + gp) * kGradStride + t * 8 + b];
-      }
-      const double p00 = ga[0] * gb[0], p11 = ga[1] * gb[1], p22 = ga[2] * gb[2];
-      blk[0][0] += (m.c11 * p00 + m.c44 * (p11 + p22)) * w;
-      blk[1][1] += (m.c11 * p11 + m.c44 * (p00 + p22)) * w;
-      blk[2][2] += (m.c11 * p22 + m.c44 * (p00 + p11)) * w;
-      blk[0][1] += (m.c12 * ga[0] * gb[1] + m.c44 * ga[1] * gb[0]) * w;
-      blk[0][2] += (m.c12 * ga[0] * gb[2] + m.c44 * ga[2] * gb[0]) * w;
-      blk[1][0] += (m.c12 * ga[1] * gb[0] + m.c44 * ga[0] * gb[1]) * w;
-      blk[1][2] += (m.c12 * ga[1] * gb[2] + m.c44 * ga[2] * gb[1]) * w;
-      blk[2][0] += (m.c12 * ga[2] * gb[0] + m.c44 * ga[0] * gb[2]) * w;
-      blk[2][1] += (m.c12 * ga[2] * gb[1] + m.c44 * ga[1] * gb[2]) * w;
-    }
-  } else {
   double S[3][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -173,16 +147,6 @@ __device__ __forceinline__ void hex8_block(const double* __restrict__ grad, cons
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       if (r != c) blk[r][c] = m.c12 * S[r][c] + m.c44 * S[c][r];
-  }
-}
-
-inline bool hex8_legacy_block() {
-  static int v = -1;
-  if (v < 0) {
-    const char* env = std::getenv("FEA_HEX8_LEGACY");
-    v = env != nullptr && env[0] == '1';
-  }
-  return v == 1;
 }
 
 }  // namespace fea

@@ -138,11 +138,9 @@ static int launch_spmm(int64_t n_nodes, const int32_t* rp, const int32_t* ci, co
                        double* Y, int R, cudaStream_t stream) {
   if (!spmm_can_vectorise(R, X, Y))
     return launch_spmm_variant<D, 1, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, X, Y, R, stream);
-  switch (spmm_variant()) {
-    case 1: return launch_spmm_variant<D, 2, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, X, Y, R, stream);
-    case 2: return launch_spmm_variant<D, 2, 1, 3, 3>(n_nodes, rp, ci, values, X, Y, R, stream);
-    default: return launch_spmm_variant<D, 2, 2, 3, 2>(n_nodes, rp, ci, values, X, Y, R, stream);
-  }
+  // node pairs per warp, 3 coupled nodes in flight (round 1 also measured groups of 4 and single nodes:
+  // 10-25 % slower, profiles/kernels_r01b_ncu.txt)
+  return launch_spmm_variant<D, 2, 2, 3, 2>(n_nodes, rp, ci, values, X, Y, R, stream);
 }
 
 extern "C" int fea_spmm(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, const int32_t* node_colidx,

@@ -403,11 +403,7 @@ static int launch_multi_spmm(int64_t n_nodes, const int32_t* rp, const int32_t* 
                              const double* P, double* AP, int R, bool vec, const MultiWork& w, cudaStream_t stream,
                              const double* Pown = nullptr) {
   if (!vec) return launch_multi_spmm_variant<D, 1, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
-  switch (spmm_variant()) {
-    case 1: return launch_multi_spmm_variant<D, 2, kSpmmGroup, 2, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
-    case 2: return launch_multi_spmm_variant<D, 2, 1, 3, 3>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
-    default: return launch_multi_spmm_variant<D, 2, 2, 3, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
-  }
+  return launch_multi_spmm_variant<D, 2, 2, 3, 2>(n_nodes, rp, ci, values, P, AP, R, w, stream, Pown);
 }
 
 // Multi-GPU driver: after the world sums of (r.z, ||b||^2) have replaced the local ones, derive the

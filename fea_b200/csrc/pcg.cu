@@ -96,6 +96,7 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
 __device__ __forceinline__ bool publish_partials(double* partials, int n_scalars, const double* vals,
                                                  uint32_t* counter, bool sys = false) {
   __shared__ bool s_last;
+  FEA_ASSERT(gridDim.x <= (unsigned)kMaxPartials && n_scalars <= 2);
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_scalars; ++s) partials[s * kMaxPartials + blockIdx.x] = vals[s];
     if (sys)

@@ -136,6 +136,7 @@ __device__ __forceinline__ void ld_volatile_v2(const unsigned long long* p, unsi
 // kernel argument the indexed array went to local memory and took the SpMV from 50 to 98 registers.)
 __device__ __forceinline__ void peer_publish(const PeerView& pv, int kind, long long k, double v0, double v1) {
   const int lane = threadIdx.x & 31;
+  FEA_ASSERT(kind >= 1 && kind <= 2 && pv.world <= kMaxPeers && pv.rank >= 0 && pv.rank < pv.world);
   if (lane < pv.world) {
     LlSlot* dst = &pv.hdr[lane]->ll[(int)(k & 1)][kind - 1][pv.rank];
     const unsigned long long f = (unsigned long long)ll_flag(pv.epoch, k) << 32;

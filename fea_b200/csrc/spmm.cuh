@@ -365,14 +365,4 @@ inline bool spmm_can_vectorise(int R, const void* X, const void* Y) {
   return R % 2 == 0 && (reinterpret_cast<uintptr_t>(X) & 15u) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0;
 }
 
-// Experiment switch (FEA_SPMM_VARIANT=0..): which build of the vector kernel the launchers pick.
-inline int spmm_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* env = std::getenv("FEA_SPMM_VARIANT");
-    v = env != nullptr ? std::atoi(env) : 0;
-  }
-  return v;
-}
-
 }  // namespace fea

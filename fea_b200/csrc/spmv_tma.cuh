@@ -195,15 +195,9 @@ __device__ __forceinline__ double row_part_dot(const double* vrow, const int32_t
 #pragma unroll
     for (int u = 0; u < kTmaUnroll; ++u) {
       const int k = k0 + u;
-#ifdef FEA_GATED_WEAK
-      if (COHERENT)
-        xv[u] = k < cnt ? xb[(int64_t)D * cols[k]] : 0.0;
-      else
-#else
       if (COHERENT)
         xv[u] = k < cnt ? __ldcg(xb + (int64_t)D * cols[k]) : 0.0;
       else
-#endif
         xv[u] = k < cnt ? __ldg(xb + (int64_t)D * cols[k]) : 0.0;
     }
 #pragma unroll
@@ -284,6 +278,9 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
           mbar_wait(&empty[s], ph ^ 1u);
           unsigned char* buf = stage0 + (size_t)s * stage_bytes;
           const uint32_t vbytes = (uint32_t)(t.v_hi - t.v_lo) * 8u, cbytes = (uint32_t)(t.c_hi - t.c_lo) * 4u;
+          FEA_ASSERT(t.v_lo >= 0 && t.v_hi >= t.v_lo && t.v_hi - t.v_lo <= val_cap && t.c_hi - t.c_lo <= col_cap);
+          FEA_ASSERT(t.v_hi <= (int64_t)DD * total_cols && t.c_hi <= total_cols && t.c_lo >= 0);
+          FEA_ASSERT(vbytes % 16 == 0 && cbytes % 16 == 0);
           mbar_expect_tx(&full[s], vbytes + cbytes);
           if (vbytes) bulk_g2s(buf, values + t.v_lo, vbytes, &full[s], policy);
           if (cbytes) bulk_g2s(buf + sizeof(double) * val_cap, node_colidx + t.c_lo, cbytes, &full[s], policy);
@@ -350,11 +347,14 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
       } else {
         const int s = q % stages;
         const uint32_t ph = (uint32_t)(q / stages) & 1u;
+        FEA_ASSERT(s % G == group % G || stages % G != 0);  // a stage is always consumed by the same group
         mbar_wait(&full[s], ph);
         if (active) {
           const unsigned char* buf = stage0 + (size_t)s * stage_bytes;
           const double* vs = reinterpret_cast<const double*>(buf) + (int)((int64_t)DD * lo - t.v_lo);
           const int32_t* cs = reinterpret_cast<const int32_t*>(buf + sizeof(double) * val_cap) + (lo - t.c_lo);
+          FEA_ASSERT((int64_t)DD * lo >= t.v_lo && (int64_t)DD * hi <= t.v_hi && lo >= t.c_lo && hi <= t.c_hi);
+          FEA_ASSERT(cnt >= 0 && (int)((int64_t)DD * lo - t.v_lo) + DD * cnt <= val_cap && (lo - t.c_lo) + cnt <= col_cap);
           part = row_part_dot<D, COHERENT>(vs + a * D * cnt, cs, cnt, b, x);
         }
         __syncwarp();
@@ -380,11 +380,7 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
     if (GATED) {
       // sweep positions [0, n_tiles - lower - upper) are interior tiles, then the upper face, then the
       // lower face (rotation above); a group that owns face tiles waits for both neighbours once
-#ifdef FEA_GATED_INTERIOR_CG
-      sweep(n_tiles - lower_tiles - upper_tiles, std::true_type{});
-#else
       sweep(n_tiles - lower_tiles - upper_tiles, std::false_type{});
-#endif
       if (tile64 < n_tiles) {  // group-uniform
         halo_gate_wait(gate, warp == group * GW && lane == 0, 1 + group, GW * 32);
         // With 128-byte aligned slab borders no line holds both owned and halo rows: halo lines are

@@ -144,13 +144,6 @@ int fea_assemble_truss(const double* nodes, const int32_t* members, const double
                        const int32_t* node_rowptr, const int32_t* node_colidx, const uint8_t* fixed,
                        int32_t mode, double* values, double* dinv, int32_t* status, void* stream);
 
-/* Scatter-add alternative for hex8 (element-parallel, FP64 atomics into `values`, which the
- * caller zeroes): same result up to summation order; kept for comparison with the gather path. */
-int fea_assemble_hex8_scatter(const double* nodes, const int32_t* elements, int64_t n_elem,
-                              double E, double nu, const int32_t* node_rowptr,
-                              const int32_t* node_colidx, double* values, int32_t* status,
-                              void* stream);
-
 /* dinv[i] = fixed[i] ? 0 : 1 / K_ii from an assembled block-pattern matrix. */
 int fea_jacobi_dinv(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_rowptr,
                     const int32_t* node_colidx, const double* values, const uint8_t* fixed,
