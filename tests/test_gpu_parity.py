@@ -125,6 +125,8 @@ def test_hex8_pattern_and_values(mods, name, case):
     K2 = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, pattern=pat)
     assert torch.equal(K.values, K2.values)
     # Dirichlet: dinv encodes the constraints; eliminated mode = identity rows/cols
+    from fea_b200 import _lib
+
     fixed = core._fixed_mask(cons, nodes.size)
     Kf = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, pattern=pat, fixed=fixed)
     dinv = Kf.dinv.cpu().numpy()
