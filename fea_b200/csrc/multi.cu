@@ -28,7 +28,13 @@ static_assert(sizeof(MultiState) == 64, "MultiState layout");
 
 struct MultiWork {
   MultiState* st;
-  double *rz, *bnorm2, *rz_new, *rr, *pap;  // R doubles each
+  double *rz, *bnorm2, *rz_new, *rr, *pap;  // R doubles each: the sums the kernels READ
+  // ... and where the reducing kernels WRITE their column sums.  One GPU: the same arrays.  Multi-GPU
+  // driver: a second set; the driver copies it over the first and all-reduces that.  A kernel that
+  // returns early (solve finished, iterations still enqueued) then leaves its local sums untouched and
+  // the world sums come out the same again -- all-reducing the shared arrays in place multiplied the
+  // frozen residuals by the world size once per left-over iteration.
+  double *l_rz, *l_bnorm2, *l_rz_new, *l_rr, *l_pap;
   int32_t *active, *iters;                  // R ints each
   double* partials;                         // kMultiBlocks * 2 * R
   double *Rv, *P, *AP;                      // n * R each
@@ -37,18 +43,20 @@ struct MultiWork {
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 static size_t multi_bytes(int64_t n, int R) {
-  return 256 + align256(sizeof(double) * 5 * R) + align256(sizeof(int32_t) * 2 * R) +
+  return 256 + align256(sizeof(double) * 10 * R) + align256(sizeof(int32_t) * 2 * R) +
          align256(sizeof(double) * (size_t)kMultiBlocks * 2 * R) + 3 * align256(sizeof(double) * (size_t)n * R);
 }
 
-static MultiWork carve_multi(void* work, int64_t n, int R) {
+static MultiWork carve_multi(void* work, int64_t n, int R, bool split = false) {
   MultiWork w;
   char* c = static_cast<char*>(work);
   w.st = reinterpret_cast<MultiState*>(c);
   c += 256;
   double* d = reinterpret_cast<double*>(c);
   w.rz = d; w.bnorm2 = d + R; w.rz_new = d + 2 * R; w.rr = d + 3 * R; w.pap = d + 4 * R;
-  c += align256(sizeof(double) * 5 * R);
+  double* l = split ? d + 5 * R : d;
+  w.l_rz = l; w.l_bnorm2 = l + R; w.l_rz_new = l + 2 * R; w.l_rr = l + 3 * R; w.l_pap = l + 4 * R;
+  c += align256(sizeof(double) * 10 * R);
   w.active = reinterpret_cast<int32_t*>(c);
   w.iters = w.active + R;
   c += align256(sizeof(int32_t) * 2 * R);
@@ -152,16 +160,16 @@ multi_init_kernel(int64_t n, int R, const double* __restrict__ B, const double* 
     fold_columns<CPL, 2>(acc, col0, R, s_cols, s_red);
   }
   if (publish_columns(w.partials, s_cols, 2, R, &w.st->counter[3])) {
-    reduce_columns(w.partials, 0, R, w.rz);
-    reduce_columns(w.partials, 1, R, w.bnorm2);
+    reduce_columns(w.partials, 0, R, w.l_rz);
+    reduce_columns(w.partials, 1, R, w.l_bnorm2);
     __syncthreads();
     const int tid = ty * 32 + tx;
     int act = 0;
     for (int col = tid; col < R; col += 256) {
-      const int a = w.bnorm2[col] > 0.0 ? 1 : 0;
+      const int a = w.l_bnorm2[col] > 0.0 ? 1 : 0;
       w.active[col] = a;
       w.iters[col] = 0;
-      w.rr[col] = w.bnorm2[col];
+      w.rr[col] = w.l_bnorm2[col];
       w.rz_new[col] = 0.0;
       w.pap[col] = 0.0;
       act += a;
@@ -204,7 +212,7 @@ multi_spmm_kernel(int64_t n_nodes, const int32_t* __restrict__ node_rowptr, cons
     fold_columns<CPL, 1>(dot, col0, R, s_cols, s_red);
   }
   if (publish_columns(w.partials, s_cols, 1, R, &w.st->counter[0])) {
-    reduce_columns(w.partials, 0, R, w.pap);
+    reduce_columns(w.partials, 0, R, w.l_pap);
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) w.st->counter[0] = 0;
   }
@@ -285,8 +293,8 @@ multi_update_kernel(int64_t n, int R, const double* __restrict__ dinv, const dou
   }
   const bool bad = s_bad != 0;
   if (publish_columns(w.partials, s_cols, 2, R, &st->counter[1])) {
-    reduce_columns(w.partials, 0, R, w.rz_new);
-    reduce_columns(w.partials, 1, R, w.rr);
+    reduce_columns(w.partials, 0, R, w.l_rz_new);
+    reduce_columns(w.partials, 1, R, w.l_rr);
     __syncthreads();
     if (tx == 0 && ty == 0) {
       st->iter += 1;
@@ -555,12 +563,15 @@ static bool multi_vec_ok(int R, const void* a, const void* b, const void* c) {
 
 extern "C" int fea_pcg_multi_layout(int32_t n_rhs, int64_t* offsets_host) {
   // byte offsets inside the workspace: [0] state (64 B: iter, done, status, max_iter, n_active, n_rhs),
-  // [1] the 5R per-column doubles rz | bnorm2 | rz_new | rr | pap, [2] active (R int32), [3] iters (R int32)
+  // [1] the 5R WORLD sums rz | bnorm2 | rz_new | rr | pap that the kernels read, [2] active (R int32),
+  // [3] iters (R int32), [4] the 5R LOCAL sums (same order) that the reducing kernels write: the driver
+  // copies [4] over [1] and all-reduces [1]
   if (!offsets_host || n_rhs < 1) return FEA_ERR_INVALID;
   offsets_host[0] = 0;
   offsets_host[1] = 256;
-  offsets_host[2] = 256 + (int64_t)align256(sizeof(double) * 5 * n_rhs);
+  offsets_host[2] = 256 + (int64_t)align256(sizeof(double) * 10 * n_rhs);
   offsets_host[3] = offsets_host[2] + (int64_t)sizeof(int32_t) * n_rhs;
+  offsets_host[4] = 256 + (int64_t)sizeof(double) * 5 * n_rhs;
   return FEA_OK;
 }
 
@@ -571,7 +582,7 @@ extern "C" int fea_pcg_multi_init(int64_t n_dof, int32_t n_rhs, const double* B,
   if (!B || !dinv || !X || !P_own || !work || n_dof <= 0 || n_rhs < 1 || n_rhs > kMaxRhs || max_iter < 1)
     return FEA_ERR_INVALID;
   if (work_bytes < multi_bytes(n_dof, n_rhs)) return FEA_ERR_WORKSPACE;
-  MultiWork w = carve_multi(work, n_dof, n_rhs);
+  MultiWork w = carve_multi(work, n_dof, n_rhs, true);
   const unsigned vb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_dof, 8 * 8), kMultiBlocks));
   FEA_TRY(check(cudaMemsetAsync(w.st, 0, 256, stream)));
   if (multi_vec_ok(n_rhs, B, X, P_own))
@@ -583,7 +594,7 @@ extern "C" int fea_pcg_multi_init(int64_t n_dof, int32_t n_rhs, const double* B,
 
 extern "C" int fea_pcg_multi_activate(int64_t n_dof, int32_t n_rhs, void* work, void* stream_) {
   if (!work || n_dof <= 0 || n_rhs < 1 || n_rhs > kMaxRhs) return FEA_ERR_INVALID;
-  multi_activate_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(carve_multi(work, n_dof, n_rhs));
+  multi_activate_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(carve_multi(work, n_dof, n_rhs, true));
   return check_launch();
 }
 
@@ -595,7 +606,7 @@ extern "C" int fea_pcg_multi_step_spmm(int64_t n_owned_nodes, int32_t d, const i
       n_rhs > kMaxRhs || p_row_offset < 0)
     return FEA_ERR_INVALID;
   const int64_t n = n_owned_nodes * d;
-  MultiWork w = carve_multi(work, n, n_rhs);
+  MultiWork w = carve_multi(work, n, n_rhs, true);
   const double* Pown = P_ext + (size_t)p_row_offset * d * n_rhs;
   const bool vec = multi_vec_ok(n_rhs, P_ext, w.AP, Pown);
   int rc;
@@ -612,7 +623,7 @@ extern "C" int fea_pcg_multi_step_spmm(int64_t n_owned_nodes, int32_t d, const i
 extern "C" int fea_pcg_multi_step_update(int64_t n_dof, int32_t n_rhs, const double* dinv, const double* P_own,
                                          double* X, void* work, void* stream_) {
   if (!dinv || !P_own || !X || !work || n_dof <= 0 || n_rhs < 1 || n_rhs > kMaxRhs) return FEA_ERR_INVALID;
-  MultiWork w = carve_multi(work, n_dof, n_rhs);
+  MultiWork w = carve_multi(work, n_dof, n_rhs, true);
   const unsigned vb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_dof, 8 * 8), kMultiBlocks));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (multi_vec_ok(n_rhs, P_own, X, w.AP))
@@ -625,7 +636,7 @@ extern "C" int fea_pcg_multi_step_update(int64_t n_dof, int32_t n_rhs, const dou
 extern "C" int fea_pcg_multi_step_direction(int64_t n_dof, int32_t n_rhs, const double* dinv, double* P_own,
                                             void* work, void* stream_) {
   if (!dinv || !P_own || !work || n_dof <= 0 || n_rhs < 1 || n_rhs > kMaxRhs) return FEA_ERR_INVALID;
-  MultiWork w = carve_multi(work, n_dof, n_rhs);
+  MultiWork w = carve_multi(work, n_dof, n_rhs, true);
   const unsigned vb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_dof, 8 * 8), kMultiBlocks));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (multi_vec_ok(n_rhs, P_own, w.Rv, w.AP))

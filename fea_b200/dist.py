@@ -667,10 +667,16 @@ def distributed_pcg_multi(K, plan: SlabPlan, B_owned: torch.Tensor, dinv_owned: 
     P_own = P_ext[plan.offset * d:plan.offset * d + n_own]
     ws_bytes = lib.fea_pcg_multi_workspace(n_own, R)
     work = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    off = (ctypes.c_int64 * 4)()
+    off = (ctypes.c_int64 * 5)()
     _lib.check(lib.fea_pcg_multi_layout(R, ctypes.addressof(off)), "fea_pcg_multi_layout")
     state = work[off[0]:off[0] + 64].view(torch.int32)
-    scal = work[off[1]:off[1] + 8 * 5 * R].view(torch.float64)
+    scal = work[off[1]:off[1] + 8 * 5 * R].view(torch.float64)    # world sums (what the kernels read)
+    local = work[off[4]:off[4] + 8 * 5 * R].view(torch.float64)   # this rank's sums (what they write)
+
+    def world_sum(lo: int, hi: int) -> None:
+        scal[lo:hi].copy_(local[lo:hi])
+        if multi:
+            dist.all_reduce(scal[lo:hi], group=group)
     iters = work[off[3]:off[3] + 4 * R].view(torch.int32)
     pt = K.pattern
     rowptr_owned = pt.node_rowptr[plan.offset:]
@@ -680,8 +686,7 @@ def distributed_pcg_multi(K, plan: SlabPlan, B_owned: torch.Tensor, dinv_owned: 
     _lib.check(lib.fea_pcg_multi_init(n_own, R, B_owned.data_ptr(), dinv_owned.data_ptr(), X.data_ptr(),
                                       P_own.data_ptr(), float(tol), int(max_iter), work.data_ptr(), ws_bytes, s()),
                "fea_pcg_multi_init")
-    if multi:
-        dist.all_reduce(scal[:2 * R], group=group)
+    world_sum(0, 2 * R)
     _lib.check(lib.fea_pcg_multi_activate(n_own, R, work.data_ptr(), s()), "fea_pcg_multi_activate")
     done_iter, finished = 0, False
     while not finished:
@@ -691,12 +696,10 @@ def distributed_pcg_multi(K, plan: SlabPlan, B_owned: torch.Tensor, dinv_owned: 
             _lib.check(lib.fea_pcg_multi_step_spmm(plan.n_owned, d, rowptr_owned.data_ptr(), pt.node_colidx.data_ptr(),
                                                    K.values.data_ptr(), P_ext.data_ptr(), plan.offset, R,
                                                    work.data_ptr(), s()), "fea_pcg_multi_step_spmm")
-            if multi:
-                dist.all_reduce(scal[4 * R:5 * R], group=group)
+            world_sum(4 * R, 5 * R)
             _lib.check(lib.fea_pcg_multi_step_update(n_own, R, dinv_owned.data_ptr(), P_own.data_ptr(), X.data_ptr(),
                                                      work.data_ptr(), s()), "fea_pcg_multi_step_update")
-            if multi:
-                dist.all_reduce(scal[2 * R:4 * R], group=group)
+            world_sum(2 * R, 4 * R)
             _lib.check(lib.fea_pcg_multi_step_direction(n_own, R, dinv_owned.data_ptr(), P_own.data_ptr(),
                                                         work.data_ptr(), s()), "fea_pcg_multi_step_direction")
         done_iter += todo

@@ -291,9 +291,11 @@ int fea_pcg_solve_p2p(int64_t n_owned_nodes, int32_t dof_per_node, const int32_t
  *                                     (n_local_dof, R) array, owned rows start at node p_row_offset
  *   fea_pcg_multi_step_update      -> sum scalars[2R .. 4R) (new r.z, r.r)
  *   fea_pcg_multi_step_direction      convergence bookkeeping on the world sums (identical everywhere)
- * `work`: fea_pcg_multi_workspace(n_owned_dof, R) bytes.  fea_pcg_multi_layout gives the byte offsets in it
- * of {state (int32: iter, done, status, max_iter, n_active, n_rhs), the 5R doubles rz | bnorm2 | rz_new |
- * rr | pap, active (R int32), iterations per column (R int32)}. */
+ * The reducing kernels write their column sums to a LOCAL set of the 5R scalars; the caller copies the
+ * local set over the WORLD set and all-reduces that (idempotent when a finished solve returns early).
+ * `work`: fea_pcg_multi_workspace(n_owned_dof, R) bytes.  fea_pcg_multi_layout fills offsets_host[5], the
+ * byte offsets in it of {state (int32: iter, done, status, max_iter, n_active, n_rhs), the 5R world doubles
+ * rz | bnorm2 | rz_new | rr | pap, active (R int32), iterations per column (R int32), the 5R local doubles}. */
 int fea_pcg_multi_layout(int32_t n_rhs, int64_t* offsets_host);
 int fea_pcg_multi_init(int64_t n_dof, int32_t n_rhs, const double* B, const double* dinv, double* X,
                        double* P_own, double tol, int32_t max_iter, void* work, size_t work_bytes,
