@@ -129,6 +129,46 @@ def test_plan_invariants():
         assert covered.sum() - elements.shape[0] == 9 * (world - 1)
 
 
+def test_default_cuts_are_balanced_and_line_aligned():
+    """default_cuts: node-balanced, multiples of 16 nodes; plan_slab then starts the local range early so
+    that the owned rows of a local vector begin and end on 128-byte boundaries (16 nodes x 3 doubles), the
+    halo ranges stay exactly what the elements need, and neighbours' send / recv ranges still match."""
+    nodes, elements, cons, forces = fo.cantilever_case(40, 8)  # 3321 nodes, 81 per layer
+    Kg = fo.assemble_csr(elements, fo.hex8_ke_batched(nodes, elements, 1.0, 0.3), nodes.shape[0], 3)
+    for world in (2, 3):
+        cuts = fdist.default_cuts(nodes.shape[0], world)
+        assert cuts[0] == 0 and cuts[-1] == nodes.shape[0] and np.all(cuts[1:-1] % 16 == 0)
+        assert np.diff(cuts).max() - np.diff(cuts).min() <= 32
+        assert np.any(cuts[1:-1] % 81 != 0)  # not layer-aligned: the cut runs through a node layer
+        plans = [fdist.plan_slab(elements, cuts, r) for r in range(world)]
+        for p in plans:
+            assert p.offset % 16 == 0
+            if p.rank < world - 1:
+                assert (p.offset + p.n_owned) % 16 == 0
+            if p.recv_up is not None:
+                assert plans[p.rank + 1].send_down == (p.rank, p.recv_up[1], p.recv_up[2])
+            if p.recv_down is not None:
+                assert plans[p.rank - 1].send_up == (p.rank, p.recv_down[1], p.recv_down[2])
+                assert p.g_lo <= p.recv_down[1] and p.recv_down[1] - p.g_lo < 16  # only the padding in front
+            el = elements[p.element_ids] - p.g_lo
+            assert el.min() >= 0 and el.max() < p.n_local
+            Kl = fo.assemble_csr(el, fo.hex8_ke_batched(nodes[p.g_lo:p.g_hi], el, 1.0, 0.3), p.n_local, 3)
+            rows = Kl[3 * p.offset:3 * (p.offset + p.n_owned)]
+            ref = Kg[3 * p.own_lo:3 * p.own_hi, 3 * p.g_lo:3 * p.g_hi]
+            assert np.array_equal(rows.indptr, ref.indptr) and np.array_equal(rows.indices, ref.indices)
+            assert np.array_equal(rows.data, ref.data)
+    # the multi-threaded host scan and the numpy path agree (Fortran-ordered input takes the numpy path)
+    cuts = fdist.default_cuts(nodes.shape[0], 3)
+    for r in range(3):
+        a, b = fdist.plan_slab(elements, cuts, r), fdist.plan_slab(np.asfortranarray(elements), cuts, r)
+        assert (a.g_lo, a.g_hi, a.send_down, a.send_up, a.recv_down, a.recv_up) == \
+               (b.g_lo, b.g_hi, b.send_down, b.send_up, b.recv_down, b.recv_up)
+        assert np.array_equal(a.element_ids, b.element_ids)
+    # small meshes are not forced onto 16-node boundaries
+    small = fdist.default_cuts(96, 4)
+    assert list(small) == [0, 24, 48, 72, 96]
+
+
 def test_thin_slab_rejected():
     nodes, elements, cons, forces = fo.cantilever_case(4, 2)
     # cuts inside a node layer: rank 0's halo would reach past rank 1 into rank 2
@@ -160,6 +200,26 @@ def _worker(rank, world, port, ret):
                                                                            dtype=torch.float64)
         fdist.HaloExchange(plan, 3)(v)
         assert torch.equal(v, torch.arange(3 * plan.g_lo, 3 * plan.g_hi, dtype=torch.float64))
+        # gather of the owned rows on rank 0 (uneven slabs), as the collective solve() does for (u, K u)
+        own = torch.arange(plan.own_lo, plan.own_hi, dtype=torch.float64)
+        both = torch.stack([own, -own]).reshape(2, plan.n_owned, 1).repeat(1, 1, 3).contiguous()
+        full = fdist.gather_rows(plan, cuts, both)
+        if rank == 0:
+            want = torch.arange(0, nodes.shape[0], dtype=torch.float64)
+            assert full.shape == (2, nodes.shape[0], 3)
+            assert torch.equal(full[0, :, 2], want) and torch.equal(full[1, :, 0], -want)
+        else:
+            assert full is None
+        # the same solve on node-balanced, 16-node aligned cuts of a larger mesh (halo narrower than the padding)
+        case2 = fo.cantilever_case(24, 6)
+        cuts2 = fdist.default_cuts(case2[0].shape[0], world) if world == 2 else fdist.node_cuts(case2[0].shape[0], world)
+        plan2 = fdist.plan_slab(case2[1], cuts2, rank)
+        K2, b2, dinv2 = local_problem(case2, plan2)
+        x2, info2 = fdist.distributed_pcg(NumpyOps(K2, plan2, 3), plan2, 3, b2, dinv2, tol=1e-12, max_iter=5000, chunk=16)
+        parts2 = [None] * world
+        dist.all_gather_object(parts2, (plan2.own_lo, x2.numpy(), info2.status))
+        if rank == 0:
+            ret["parts2"] = parts2
     finally:
         dist.destroy_process_group()
 
@@ -183,3 +243,9 @@ def test_distributed_pcg_gloo(world):
     assert abs(iters.pop() - io["iterations"]) <= 3
     assert np.abs(u - uo.ravel()).max() <= 1e-10 * np.abs(uo).max()
     assert np.abs(u - ud.ravel()).max() <= 1e-8 * np.abs(ud).max()
+    parts2 = sorted(ret["parts2"], key=lambda t: t[0])
+    assert all(p[2] == 0 for p in parts2)
+    n2, e2, c2, f2 = fo.cantilever_case(24, 6)
+    ud2, _, _ = fo.solve_hex8(n2, e2, c2, f2, method="direct")
+    u2 = np.concatenate([p[1] for p in parts2])
+    assert np.abs(u2 - ud2.ravel()).max() <= 1e-8 * np.abs(ud2).max()
