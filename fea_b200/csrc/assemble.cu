@@ -40,12 +40,12 @@ __device__ __forceinline__ double eliminate(double v, const uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------
 constexpr int kAsmWarps = 4;
 
-__global__ void __launch_bounds__(kAsmWarps * 32)
+__global__ void __launch_bounds__(kAsmWarps * 32, 4)
 assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ elements, int64_t n_nodes,
                      Hex8Material mat, const int32_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e,
                      const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx, int maxc,
                      const uint8_t* __restrict__ fixed, int mode, double* __restrict__ values,
-                     double* __restrict__ dinv, int32_t* status) {
+                     double* __restrict__ dinv, const uint8_t* __restrict__ todo, int32_t* status) {
   extern __shared__ double s_dyn[];
   // layout: shape table | per warp: grad, detj, acc[9*maxc], cols[maxc] (ints, padded to doubles)
   double* s_tab = s_dyn;
@@ -59,8 +59,15 @@ assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict
   hex8_fill_shape_table(s_tab);
   __syncthreads();
 
-  for (int64_t node = (int64_t)blockIdx.x * kAsmWarps + warp; node < n_nodes;
-       node += (int64_t)gridDim.x * kAsmWarps) {
+  // a warp takes 8 consecutive nodes per trip and works through those still to do (all of them without
+  // `todo`; with it, the nodes assemble_hex8_affine_kernel left: one coalesced flag load per 8 nodes)
+  for (int64_t base = ((int64_t)blockIdx.x * kAsmWarps + warp) * 8; base < n_nodes;
+       base += (int64_t)gridDim.x * kAsmWarps * 8) {
+    const bool mine = lane < 8 && base + lane < n_nodes && (todo == nullptr || todo[base + lane] != 0);
+    unsigned pending = __ballot_sync(kFull, mine);
+  while (pending != 0) {
+    const int64_t node = base + (__ffs(pending) - 1);
+    pending &= pending - 1;
     const int lo = node_rowptr[node];
     const int cnt = node_rowptr[node + 1] - lo;
     const int row_len = 3 * cnt;
@@ -126,6 +133,240 @@ assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict
         di = is_fixed ? 0.0 : 1.0 / diag;
       }
       dinv[3 * node + lane] = di;
+    }
+    __syncwarp();
+  }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// hex8, exactly affine elements (parallelepipeds: every element of an extruded grid).  The trilinear
+// map x(xi,eta,zeta) = sum_m c_m * monomial_m has its 8 coefficient vectors c_m = the Walsh-Hadamard
+// transform of the corner coordinates over the three sign bits of the local node.  When the four
+// higher coefficients (xi.eta, xi.zeta, eta.zeta, xi.eta.zeta) are EXACTLY zero the Jacobian is the
+// same at all Gauss points and the quadrature of utils.py:200-237 collapses to
+//     S_ab = sum_gp detJ g_a g_b^T = 1/(8 detJc) * adj(Jc) M_ab adj(Jc)^T,      Jc = 8 J = [c_xi; c_eta; c_zeta]
+// with the constant table M_ab = sum_gp dN_a dN_b^T: 54 FMA per 3x3 block and no per-Gauss-point geometry
+// at all (the general kernel spends 2/3 of its FP64 instructions there, once per incident NODE).
+//
+// Pass 0 (hex8_affine_geometry_kernel, thread per element): adj(Jc) and 1/(8 detJc) -- 80 bytes per element in
+// a stream-ordered scratch array; scale = -1 marks an element that is not exactly affine.  Geometry is
+// evaluated ONCE per element here; the owner-computes gather below only reads it (L2-resident reuse).
+// Pass 1 (assemble_hex8_affine_kernel): a warp owns 4 consecutive nodes; lane = (node q, column node j).
+// Round k handles the k-th incident element of each of the 4 nodes; lane j evaluates the block K_{a_own, j}.
+// Rounds are ascending element order per node -- the reference's summation order (cubebeam.py:82-90) -- and
+// inside a round the 8 column nodes of an element are distinct, so accumulation needs no serialisation and no
+// atomics.  A node with any non-affine incident element is left to assemble_hex8_kernel (flag in `todo`): the
+// choice depends on the node's own elements only, so rows stay independent of the GPU partition.
+// ------------------------------------------------------------------------------------------
+constexpr int kAffWarps = 4;
+constexpr int kAffNodes = 4;   // nodes per warp
+constexpr int kMtab = 64 * 9;  // M_ab[k][l], a-major
+constexpr int kGeomDoubles = 10;
+
+__global__ void __launch_bounds__(256)
+hex8_affine_geometry_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ elements, int64_t n_elem,
+                            double* __restrict__ geom, int32_t* status) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  // c[m] = corner whose (x, y, z) sign bits are the bits of m (hex8.cuh: kSignX/Y/Z)
+  double c[8][3];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int corner = (m & 4) | ((m & 3) ^ ((m >> 1) & 1));
+    const double* x = nodes + 3 * (int64_t)elements[e * 8 + corner];
+    c[m][0] = x[0];
+    c[m][1] = x[1];
+    c[m][2] = x[2];
+  }
+#pragma unroll
+  for (int bit = 1; bit < 8; bit <<= 1)
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+      if (!(m & bit)) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double lo = c[m][k], hi = c[m | bit][k];
+          c[m][k] = lo + hi;
+          c[m | bit][k] = hi - lo;
+        }
+      }
+  bool affine = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) affine = affine && c[3][k] == 0.0 && c[5][k] == 0.0 && c[6][k] == 0.0 && c[7][k] == 0.0;
+  const double(&J0)[3] = c[1];
+  const double(&J1)[3] = c[2];
+  const double(&J2)[3] = c[4];
+  double A[9];  // adjugate of Jc, row-major
+  A[0] = J1[1] * J2[2] - J1[2] * J2[1];
+  A[3] = J1[2] * J2[0] - J1[0] * J2[2];
+  A[6] = J1[0] * J2[1] - J1[1] * J2[0];
+  A[1] = J0[2] * J2[1] - J0[1] * J2[2];
+  A[4] = J0[0] * J2[2] - J0[2] * J2[0];
+  A[7] = J0[1] * J2[0] - J0[0] * J2[1];
+  A[2] = J0[1] * J1[2] - J0[2] * J1[1];
+  A[5] = J0[2] * J1[0] - J0[0] * J1[2];
+  A[8] = J0[0] * J1[1] - J0[1] * J1[0];
+  const double det = J0[0] * A[0] + J0[1] * A[3] + J0[2] * A[6];
+  double scale = -1.0;
+  if (affine) {
+    if (det > 0.0) scale = 0.125 / det;
+    else raise_status(status, FEA_ERR_JACOBIAN, (int)e);
+  }
+  double* out = geom + e * kGeomDoubles;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[k] = A[k];
+  out[9] = scale;
+}
+
+// Position of `key` in a sorted list padded to 32 entries with INT32_MAX: five loads, no branches.
+__device__ __forceinline__ int find_slot32(const int32_t* cols, int key) {
+  int pos = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1)
+    if (cols[pos + step - 1] < key) pos += step;
+  return pos;
+}
+
+__host__ __device__ constexpr int aff_cols_ints(int maxc) { return maxc < 32 ? 32 : ((maxc + 1) / 2) * 2; }
+
+struct AffGeom {
+  double2 a01, a23, a45, a67, a8s;  // adj(Jc) row-major, then 1/(8 detJc)
+};
+__device__ __forceinline__ AffGeom load_geom(const double* __restrict__ geom, int e) {
+  const double2* g = reinterpret_cast<const double2*>(geom + (int64_t)e * kGeomDoubles);
+  AffGeom r;
+  r.a01 = __ldg(g);
+  r.a23 = __ldg(g + 1);
+  r.a45 = __ldg(g + 2);
+  r.a67 = __ldg(g + 3);
+  r.a8s = __ldg(g + 4);
+  return r;
+}
+
+__global__ void __launch_bounds__(kAffWarps * 32, 5)
+assemble_hex8_affine_kernel(const double* __restrict__ geom, const int32_t* __restrict__ elements, int64_t n_nodes,
+                            Hex8Material mat, const int32_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e,
+                            const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx,
+                            int maxc, const uint8_t* __restrict__ fixed, int mode, double* __restrict__ values,
+                            double* __restrict__ dinv, uint8_t* __restrict__ todo) {
+  extern __shared__ __align__(16) double s_dyn[];
+  // layout: M table | per (warp, node): acc[9*maxc] ... | cols[aff_cols_ints] ...
+  double* s_m = s_dyn;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = lane >> 3, j = lane & 7;
+  const int slot_id = warp * kAffNodes + q;
+  double* acc = s_dyn + kMtab + (size_t)slot_id * 9 * maxc;
+  int32_t* cols = reinterpret_cast<int32_t*>(s_dyn + kMtab + (size_t)kAffWarps * kAffNodes * 9 * maxc) +
+                  (size_t)slot_id * aff_cols_ints(maxc);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    const int a = i >> 3, b = i & 7;
+    double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int gp = 0; gp < 8; ++gp) {
+      double da[3], db[3];
+      hex8_shape_derivative(gp, a, da);
+      hex8_shape_derivative(gp, b, db);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) m[3 * k + l] = fma(da[k], db[l], m[3 * k + l]);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_m[i * 9 + k] = m[k];
+  }
+  __syncthreads();
+  const bool small_rows = maxc <= 32;
+
+  const int64_t n_groups = (n_nodes + kAffNodes - 1) / kAffNodes;
+  for (int64_t g = (int64_t)blockIdx.x * kAffWarps + warp; g < n_groups; g += (int64_t)gridDim.x * kAffWarps) {
+    const int64_t node = g * kAffNodes + q;
+    const bool valid = node < n_nodes;
+    int lo = 0, cnt = 0, inc_lo = 0, deg = 0;
+    if (valid) {
+      lo = node_rowptr[node];
+      cnt = node_rowptr[node + 1] - lo;
+      inc_lo = n2e_ptr[node];
+      deg = n2e_ptr[node + 1] - inc_lo;
+    }
+    const int row_len = 3 * cnt;
+    for (int i = j; i < cnt; i += 8) cols[i] = node_colidx[lo + i];
+    if (small_rows)
+      for (int i = cnt + j; i < 32; i += 8) cols[i] = INT32_MAX;
+    for (int i = j; i < 9 * cnt; i += 8) acc[i] = 0.0;
+    const int max_deg = warp_max_i(deg);
+    bool dead = false;  // uniform inside a group
+    __syncwarp();
+
+    // Rounds in chunks of 8 (one incidence entry per lane of the group); the geometry record and the column node
+    // of round k+1 are in flight during the arithmetic of round k.  Lanes without work read element 0.
+    for (int k0 = 0; k0 < max_deg; k0 += 8) {
+      const int my_inc = k0 + j < deg ? n2e[inc_lo + k0 + j] : -1;
+      int inc_n = __shfl_sync(kFull, my_inc, 8 * q);
+      AffGeom g_n = load_geom(geom, max(inc_n, 0) >> 3);
+      int col_n = elements[(int64_t)(max(inc_n, 0) >> 3) * 8 + j];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        if (k0 + kk >= max_deg) break;  // warp-uniform
+        const int inc = inc_n, col = col_n;
+        const AffGeom G = g_n;
+        if (kk + 1 < 8) {
+          inc_n = __shfl_sync(kFull, my_inc, 8 * q + kk + 1);
+          g_n = load_geom(geom, max(inc_n, 0) >> 3);
+          col_n = elements[(int64_t)(max(inc_n, 0) >> 3) * 8 + j];
+        }
+        const double scale = G.a8s.y;
+        if (inc >= 0 && !(scale > 0.0)) dead = true;  // same record for the whole group
+        if (inc >= 0 && !dead) {
+          const int slot = small_rows ? find_slot32(cols, col) : find_slot(cols, cnt, col);
+          FEA_ASSERT(slot >= 0 && slot < cnt && cols[slot] == col);
+          const double A[3][3] = {{G.a01.x, G.a01.y, G.a23.x}, {G.a23.y, G.a45.x, G.a45.y}, {G.a67.x, G.a67.y, G.a8s.x}};
+          const double* M = s_m + ((inc & 7) * 8 + j) * 9;
+          double W[3][3], S[3][3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) W[r][l] = A[r][0] * M[l] + A[r][1] * M[3 + l] + A[r][2] * M[6 + l];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) S[r][c] = W[r][0] * A[c][0] + W[r][1] * A[c][1] + W[r][2] * A[c][2];
+          const double c11 = mat.c11 * scale, c12 = mat.c12 * scale, c44 = mat.c44 * scale;
+          double* dst = acc + 3 * slot;
+          dst[0] += c11 * S[0][0] + c44 * (S[1][1] + S[2][2]);
+          dst[row_len + 1] += c11 * S[1][1] + c44 * (S[0][0] + S[2][2]);
+          dst[2 * row_len + 2] += c11 * S[2][2] + c44 * (S[0][0] + S[1][1]);
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              if (r != c) dst[r * row_len + c] += c12 * S[r][c] + c44 * S[c][r];
+        }
+        __syncwarp();
+      }
+    }
+
+    if (valid && j == 0) todo[node] = dead ? 1 : 0;
+    if (valid && !dead) {
+      const int64_t base = 9 * (int64_t)lo;
+      if (mode == FEA_ASSEMBLE_ELIMINATED && fixed != nullptr) {
+        for (int i = j; i < 9 * cnt; i += 8) {
+          const int r = i / row_len, within = i - r * row_len;
+          const int kk = within / 3, c = within - 3 * kk;
+          values[base + i] = eliminate(acc[i], fixed, 3 * node + r, 3 * (int64_t)cols[kk] + c);
+        }
+      } else {
+        for (int i = j; i < 9 * cnt; i += 8) values[base + i] = acc[i];
+      }
+      if (dinv != nullptr && j < 3) {
+        double di = 0.0;  // a node no element references keeps u = 0
+        if (cnt > 0) {
+          const int kd = find_slot(cols, cnt, (int)node);
+          const double diag = acc[j * row_len + 3 * kd + j];
+          const bool is_fixed = fixed != nullptr && fixed[3 * node + j];
+          di = is_fixed ? 0.0 : 1.0 / diag;
+        }
+        dinv[3 * node + j] = di;
+      }
     }
     __syncwarp();
   }
@@ -265,6 +506,12 @@ jacobi_dinv_kernel(int64_t n_nodes, int d, const int32_t* __restrict__ node_rowp
 
 using namespace fea;
 
+// FEA_ASSEMBLE_AFFINE=0: every node through the general kernel (A/B switch).
+static bool affine_pass_disabled() {
+  const char* v = std::getenv("FEA_ASSEMBLE_AFFINE");
+  return v != nullptr && v[0] == '0';
+}
+
 extern "C" int fea_assemble_hex8(const double* nodes, const int32_t* elements, int64_t n_elem, int64_t n_nodes,
                                  double E, double nu, const int32_t* n2e_ptr, const int32_t* n2e,
                                  const int32_t* node_rowptr, const int32_t* node_colidx, int32_t max_coupled,
@@ -280,11 +527,45 @@ extern "C" int fea_assemble_hex8(const double* nodes, const int32_t* elements, i
   if (smem > 48 * 1024) {
     FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   }
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, kAsmWarps), 148LL * 64);
+  // Pass 0 + 1: nodes whose incident elements are all exactly affine (hex8_affine_geometry_kernel,
+  // assemble_hex8_affine_kernel); a per-node flag is left for the others.  Pass 2: the general kernel on those.
+  uint8_t* todo = nullptr;
+  double* geom = nullptr;
+  const size_t smem_aff =
+      sizeof(double) * (kMtab + (size_t)kAffWarps * kAffNodes * (9 * (size_t)maxc + aff_cols_ints(maxc) / 2));
+  int launches = 1;
+  if (smem_aff <= 100 * 1024 && n_elem > 0 && !affine_pass_disabled()) {
+    // stream-ordered scratch from the device's default pool (80 B per element + 1 B per node); the pool keeps what
+    // it has handed out once (release threshold), so that an assembly does not pay an OS allocation per call
+    int dev = 0;
+    cudaMemPool_t pool = nullptr;
+    FEA_TRY(check(cudaGetDevice(&dev)));
+    FEA_TRY(check(cudaDeviceGetDefaultMemPool(&pool, dev)));
+    uint64_t keep = 1ull << 31;
+    FEA_TRY(check(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)));
+    const size_t geom_bytes = sizeof(double) * kGeomDoubles * (size_t)n_elem;
+    FEA_TRY(check(cudaMallocAsync(&geom, geom_bytes + (size_t)n_nodes, stream)));
+    todo = reinterpret_cast<uint8_t*>(geom) + geom_bytes;
+    hex8_affine_geometry_kernel<<<(unsigned)ceil_div(n_elem, 256), 256, 0, stream>>>(nodes, elements, n_elem, geom,
+                                                                                    status);
+    if (smem_aff > 48 * 1024) {
+      FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_aff)));
+    }
+    const int64_t n_groups = ceil_div(n_nodes, kAffNodes);
+    const unsigned blocks_aff = (unsigned)std::min<int64_t>(ceil_div(n_groups, kAffWarps), 148LL * 64);
+    assemble_hex8_affine_kernel<<<blocks_aff, kAffWarps * 32, smem_aff, stream>>>(
+        geom, elements, n_nodes, hex8_material(E, nu), n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed, mode,
+        values, dinv, todo);
+    launches = 3;
+  }
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, kAsmWarps * 8), 148LL * 64);
   assemble_hex8_kernel<<<blocks, kAsmWarps * 32, smem, stream>>>(nodes, elements, n_nodes, hex8_material(E, nu), n2e_ptr,
                                                                  n2e, node_rowptr, node_colidx, maxc, fixed, mode, values,
-                                                                 dinv, status);
-  return check_launch();
+                                                                 dinv, todo, status);
+  const int rc = check_launch(launches);
+  if (geom != nullptr) FEA_TRY(check(cudaFreeAsync(geom, stream)));
+  return rc;
 }
 
 template <class Op>

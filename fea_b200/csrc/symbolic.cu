@@ -211,6 +211,54 @@ __global__ void __launch_bounds__(128) node_neighbors_kernel(const int32_t* __re
     const int lo = n2e_ptr[node];
     const int deg = n2e_ptr[node + 1] - lo;
     const int n = deg * npe;
+    if (n <= 64) {
+      // Register path (every node of a hex8 grid: 8 elements x 8 nodes): bitonic network over 64 keys, two per
+      // lane (key i lives in lane i & 31, register i >> 5), padded with INT32_MAX; then heads of runs are
+      // counted / written in order.  Same sorted-unique list as the rank sort below, at a third of its cost.
+      int v[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int q = lane + 32 * r;
+        v[r] = INT32_MAX;
+        if (q < n) {
+          const int t = q / npe, b = q - t * npe;
+          v[r] = elements[(int64_t)(n2e[lo + t] / npe) * npe + b];
+        }
+      }
+#pragma unroll
+      for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+          if (jj == 32) {
+            const int a = min(v[0], v[1]), b = max(v[0], v[1]);
+            v[0] = a;
+            v[1] = b;
+          } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {  // key index i = lane + 32 r: ascending run iff (i & k) == 0
+              const bool up = k == 64 || (k == 32 ? r == 0 : (lane & k) == 0);
+              const bool keep_min = ((lane & jj) == 0) == up;
+              const int o = __shfl_xor_sync(kFull, v[r], jj);
+              v[r] = keep_min ? min(v[r], o) : max(v[r], o);
+            }
+          }
+        }
+      }
+      const int p0 = __shfl_up_sync(kFull, v[0], 1), p1 = __shfl_up_sync(kFull, v[1], 1);
+      const int last0 = __shfl_sync(kFull, v[0], 31);
+      const bool h0 = v[0] != INT32_MAX && (lane == 0 || v[0] != p0);
+      const bool h1 = v[1] != INT32_MAX && v[1] != (lane == 0 ? last0 : p1);
+      const unsigned m0 = __ballot_sync(kFull, h0), m1 = __ballot_sync(kFull, h1);
+      if (WRITE) {
+        const int base_out = node_rowptr[node];
+        const unsigned below = (1u << lane) - 1u;
+        if (h0) out[base_out + __popc(m0 & below)] = v[0];
+        if (h1) out[base_out + __popc(m0) + __popc(m1 & below)] = v[1];
+      } else if (lane == 0) {
+        out[node] = __popc(m0) + __popc(m1);
+      }
+      continue;
+    }
     for (int q = lane; q < n; q += 32) {
       const int t = q / npe, b = q - t * npe;
       const int e = n2e[lo + t] / npe;

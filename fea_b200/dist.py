@@ -688,21 +688,42 @@ def distributed_pcg_multi(K, plan: SlabPlan, B_owned: torch.Tensor, dinv_owned: 
                "fea_pcg_multi_init")
     world_sum(0, 2 * R)
     _lib.check(lib.fea_pcg_multi_activate(n_own, R, work.data_ptr(), s()), "fea_pcg_multi_activate")
+    def iteration() -> None:
+        halo(P_ext)
+        _lib.check(lib.fea_pcg_multi_step_spmm(plan.n_owned, d, rowptr_owned.data_ptr(), pt.node_colidx.data_ptr(),
+                                               K.values.data_ptr(), P_ext.data_ptr(), plan.offset, R,
+                                               work.data_ptr(), s()), "fea_pcg_multi_step_spmm")
+        world_sum(4 * R, 5 * R)
+        _lib.check(lib.fea_pcg_multi_step_update(n_own, R, dinv_owned.data_ptr(), P_own.data_ptr(), X.data_ptr(),
+                                                 work.data_ptr(), s()), "fea_pcg_multi_step_update")
+        world_sum(2 * R, 4 * R)
+        _lib.check(lib.fea_pcg_multi_step_direction(n_own, R, dinv_owned.data_ptr(), P_own.data_ptr(),
+                                                    work.data_ptr(), s()), "fea_pcg_multi_step_direction")
+
+    # One CUDA graph per chunk of iterations (kernels, the NCCL halo send/recv and the per-column all-reduces
+    # captured together): the eager loop issues ~20 host operations per iteration and was host-bound beyond 2 ranks.
+    # Every step kernel starts with `if (done) return` and the exchanges are idempotent after convergence, so
+    # replaying a whole chunk past the last iteration is harmless.  The first chunk runs eagerly (NCCL sets up its
+    # point-to-point channels on first use, which cannot happen inside a capture).
+    use_graph = (multi and dev.type == "cuda" and dist.get_backend(group) == "nccl"
+                 and os.environ.get("FEA_MULTI_GRAPH", "1") != "0")
+    graph = None
     done_iter, finished = 0, False
     while not finished:
-        todo = min(chunk, max_iter - done_iter)
-        for _ in range(todo):
-            halo(P_ext)
-            _lib.check(lib.fea_pcg_multi_step_spmm(plan.n_owned, d, rowptr_owned.data_ptr(), pt.node_colidx.data_ptr(),
-                                                   K.values.data_ptr(), P_ext.data_ptr(), plan.offset, R,
-                                                   work.data_ptr(), s()), "fea_pcg_multi_step_spmm")
-            world_sum(4 * R, 5 * R)
-            _lib.check(lib.fea_pcg_multi_step_update(n_own, R, dinv_owned.data_ptr(), P_own.data_ptr(), X.data_ptr(),
-                                                     work.data_ptr(), s()), "fea_pcg_multi_step_update")
-            world_sum(2 * R, 4 * R)
-            _lib.check(lib.fea_pcg_multi_step_direction(n_own, R, dinv_owned.data_ptr(), P_own.data_ptr(),
-                                                        work.data_ptr(), s()), "fea_pcg_multi_step_direction")
-        done_iter += todo
+        if use_graph and done_iter > 0:
+            if graph is None:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    for _ in range(chunk):
+                        iteration()
+            graph.replay()
+            done_iter += chunk
+        else:
+            todo = min(chunk, max_iter - done_iter)
+            for _ in range(todo):
+                iteration()
+            done_iter += todo
         st = state.cpu()  # one synchronisation per chunk; the decisions are identical on every rank
         finished = bool(int(st[1]) != 0) or done_iter >= max_iter
     st = state.cpu()

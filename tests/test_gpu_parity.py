@@ -147,6 +147,40 @@ def test_hex8_pattern_and_values(mods, name, case):
     assert np.array_equal(Ke[fx][:, fx].diagonal(), np.ones(fx.size))
 
 
+def test_hex8_affine_pass_vs_general(mods, monkeypatch):
+    """Nodes whose incident elements are all exactly affine take the closed-form pass
+    (assemble_hex8_affine_kernel), the others the Gauss-point kernel: same matrix to rounding, rows of
+    the non-affine part bit-identical whether or not the affine pass ran, and the split is per node
+    (a half-jittered mesh exercises affine, mixed and general nodes in one assembly)."""
+    core = mods["core"]
+    nodes, elements, cons, forces = fo.cantilever_case(12, 5)
+    rng = np.random.default_rng(11)
+    h = 0.1 / 5
+    moved = nodes[:, 2] > 0.55
+    nodes = nodes.copy()
+    nodes[moved] += rng.uniform(-0.2 * h, 0.2 * h, size=(int(moved.sum()), 3))
+    nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
+    pat = core.symbolic(el, nodes.shape[0])
+    fixed = core._fixed_mask(cons, nodes.size)
+    Kref = fo.assemble_csr(elements, fo.hex8_ke_batched(nodes, elements, fo.E_HEX, fo.NU_HEX), nodes.shape[0], 3)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FEA_ASSEMBLE_AFFINE", flag)
+        K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, pattern=pat, fixed=fixed)
+        out[flag] = (K.values.cpu().numpy(), K.dinv.cpu().numpy())
+        assert np.abs(out[flag][0] - Kref.data).max() / np.abs(Kref.data).max() < KE_RTOL
+    v1, v0 = out["1"][0], out["0"][0]
+    assert np.abs(v1 - v0).max() / np.abs(v0).max() < 1e-14
+    assert rel(out["1"][1], out["0"][1]) < 1e-13
+    # rows of nodes with a jittered incident element: untouched by the affine pass, bit for bit
+    touched = np.zeros(nodes.shape[0], bool)
+    touched[elements[moved[elements].any(axis=1)].ravel()] = True
+    rp = pat.node_rowptr.cpu().numpy().astype(np.int64)
+    general_rows = np.concatenate([np.arange(9 * rp[i], 9 * rp[i + 1]) for i in np.flatnonzero(touched)])
+    assert np.array_equal(v1[general_rows], v0[general_rows])
+    assert 0 < touched.sum() < nodes.shape[0] and not np.array_equal(v1, v0)
+
+
 def test_inverted_element_in_assembly_raises(mods):
     nodes, elements, cons, forces = fo.cantilever_case(3, 2)
     elements = elements.copy()
