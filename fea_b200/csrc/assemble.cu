@@ -228,7 +228,10 @@ __device__ __forceinline__ int find_slot32(const int32_t* cols, int key) {
   return pos;
 }
 
-__host__ __device__ constexpr int aff_cols_ints(int maxc) { return maxc < 32 ? 32 : ((maxc + 1) / 2) * 2; }
+// ints per node for the column list: >= 32 (find_slot32 reads the padding), odd stride in banks so that the four
+// groups of a warp, which probe the same positions of their own lists, land on different banks; the region sits at
+// the end of the shared-memory block, so it needs no 8-byte alignment per node
+__host__ __device__ constexpr int aff_cols_ints(int maxc) { return (maxc < 32 ? 32 : maxc) | 1; }
 
 struct AffGeom {
   double2 a01, a23, a45, a67, a8s;  // adj(Jc) row-major, then 1/(8 detJc)
@@ -532,7 +535,7 @@ extern "C" int fea_assemble_hex8(const double* nodes, const int32_t* elements, i
   uint8_t* todo = nullptr;
   double* geom = nullptr;
   const size_t smem_aff =
-      sizeof(double) * (kMtab + (size_t)kAffWarps * kAffNodes * (9 * (size_t)maxc + aff_cols_ints(maxc) / 2));
+      sizeof(double) * (kMtab + (size_t)kAffWarps * kAffNodes * (9 * (size_t)maxc + (aff_cols_ints(maxc) + 1) / 2));
   int launches = 1;
   if (smem_aff <= 100 * 1024 && n_elem > 0 && !affine_pass_disabled()) {
     // stream-ordered scratch from the device's default pool (80 B per element + 1 B per node); the pool keeps what

@@ -168,6 +168,31 @@ __device__ __forceinline__ double cube_rn(double x) {
   return __dadd_rn(q, __dadd_rn(qe, __dmul_rn(pe, x)));
 }
 
+// Programmatic dependent launch (sm_90+).  A kernel of the PCG iteration lets the NEXT kernel of the stream be
+// scheduled as soon as all of its own CTAs are running (launch_dependents, first instruction), and waits for the
+// PREVIOUS kernel to have completed and flushed (wait) before it touches anything that kernel wrote: launch
+// latency, CTA scheduling and each kernel's prologue then overlap the tail of the kernel before.  Both are no-ops
+// in a kernel that was launched without cudaLaunchAttributeProgrammaticStreamSerialization.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Kernel launch with or without the programmatic-serialisation attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Streaming (evict-first) loads for data read exactly once per kernel: keeps L2 for the vectors.
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }

@@ -52,7 +52,8 @@ int current_device() {
   return dev < 0 || dev >= kMaxDevices ? 0 : dev;
 }
 
-TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_colidx, int64_t n_nodes) {
+TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_colidx, int64_t n_nodes,
+                 bool small_problem) {
   TmaPlan plan;
   plan.ok = false;
   plan.max_grid = 0;
@@ -65,6 +66,10 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
   if (n_nodes >= (int64_t)INT32_MAX / 4) return plan;
   // Shape of the pipeline: consumer groups per CTA, ring stages per CTA, CTAs (rings) per SM.
   int cfg_groups = 2, cfg_stages = 2, cfg_ctas = 3;  // best of the sweep on B200: profiles/tma_sweep_r01.log
+  // A few tiles per consumer group (a 133 k-DOF mesh has 2784 tiles for 888 groups) leave the 2-stage rings no
+  // prefetch depth and a 4-against-3 tile imbalance: 3 groups x 3 stages on 2 CTAs per SM measured -7 % per PCG
+  // iteration at 31 k / 133 k DOF and -2 % at 0.4 M / 1 M DOF (profiles/small_mesh_sweep_r02.txt).
+  if (small_problem) cfg_groups = 3, cfg_stages = 3, cfg_ctas = 2;
   if (const char* env = std::getenv("FEA_TMA_CFG")) {
     int g = 0, s = 0, c = 0;
     if (std::sscanf(env, "%d,%d,%d", &g, &s, &c) == 3 && g >= 1 && g <= kTmaMaxGroups && s >= 1 &&
@@ -86,6 +91,15 @@ TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_co
   plan.max_grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)di->sm_count * cfg_ctas));
   plan.groups = groups;
   plan.ok = true;
+  // L2 policy of the matrix stream: a matrix that fits in L2 next to the solver's vectors is kept there between the
+  // SpMVs of a solve (evict-last: -5 % per iteration at 133 k DOF / 85 MB); anything larger is streamed evict-first so
+  // that L2 keeps the gathered vector instead (evict-last costs +9 % at 0.4 M DOF / 280 MB).  Upper bound of the
+  // matrix bytes from the widest row.  FEA_TMA_L2=0|1|2 overrides (evict-first / normal / evict-last).
+  const double matrix_bytes = (double)n_nodes * max_coupled * (8.0 * d * d + 4.0);
+  plan.l2_hint = matrix_bytes <= 100e6 ? 2 : 0;
+  if (const char* env = std::getenv("FEA_TMA_L2")) {
+    if (env[0] >= '0' && env[0] <= '2') plan.l2_hint = env[0] - '0';
+  }
   return plan;
 }
 
@@ -208,6 +222,8 @@ pcg_spmv_tma_kernel(int n_nodes, const int32_t* __restrict__ node_rowptr, const 
                     double* partials, const PeerView* pv, PeerKey key) {
   extern __shared__ __align__(128) unsigned char s_tma[];
   __shared__ double s_red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->done) return;
   double dot = 0.0;
   HaloGate gate{};
@@ -271,16 +287,17 @@ static int launch_tma(const TmaPlan& plan, bool dot, int64_t n_nodes, const int3
     static GridCache cache;
     FEA_TRY(tma_grid(cache, pcg_spmv_tma_kernel<D, G, true>, plan, tma_threads(D, G), &grid));
     pcg_spmv_tma_kernel<D, G, true><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(
-        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, peer->view, peer->key);
+        n, rp, ci, values, x, y, x + off * D, L.stages | (plan.l2_hint << kTmaHintShift), L.val_cap, L.col_cap, st, partials, peer->view, peer->key);
   } else if (dot) {
     static GridCache cache;
     FEA_TRY(tma_grid(cache, pcg_spmv_tma_kernel<D, G, false>, plan, tma_threads(D, G), &grid));
-    pcg_spmv_tma_kernel<D, G, false><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(
-        n, rp, ci, values, x, y, x + off * D, L.stages, L.val_cap, L.col_cap, st, partials, nullptr, PeerKey{});
+    FEA_TRY(check(launch_kernel(pcg_spmv_tma_kernel<D, G, false>, dim3(grid), dim3(tma_threads(D, G)), L.smem_bytes,
+                                stream, plan.pdl, n, rp, ci, values, x, y, x + off * D, L.stages | (plan.l2_hint << kTmaHintShift), L.val_cap, L.col_cap,
+                                st, partials, (const PeerView*)nullptr, PeerKey{})));
   } else {
     static GridCache cache;
     FEA_TRY(tma_grid(cache, spmv_tma_kernel<D, G>, plan, tma_threads(D, G), &grid));
-    spmv_tma_kernel<D, G><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(n, rp, ci, values, x, y, L.stages,
+    spmv_tma_kernel<D, G><<<grid, tma_threads(D, G), L.smem_bytes, stream>>>(n, rp, ci, values, x, y, L.stages | (plan.l2_hint << kTmaHintShift),
                                                                         L.val_cap, L.col_cap);
   }
   return FEA_OK;
@@ -343,6 +360,8 @@ pcg_update_kernel(int64_t n, const double* __restrict__ dinv, const double* __re
   __shared__ double s_red[32];
   __shared__ double s_glob[2];
   __shared__ int s_ok;
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->done) return;
   double pap = st->pap;
   const double rz = st->rz;
@@ -438,6 +457,8 @@ pcg_direction_kernel(int64_t n, const double* __restrict__ dinv, const double* _
   __shared__ bool s_last;
   __shared__ double s_glob[2];
   __shared__ int s_ok;
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->done) return;
   const double rz = st->rz;
   double rz_new = st->rz_new, rr = st->rr;
@@ -532,6 +553,8 @@ pcg_cgcg_kernel(int64_t n, const double* __restrict__ dinv, double* __restrict__
   __shared__ double s_red[32];
   __shared__ double s_glob[3];
   __shared__ int s_ok;
+  pdl_launch_dependents();
+  pdl_wait();
   if (st->done) return;
   const int32_t iter = st->iter;  // iterations completed so far
   double gamma = iter == 0 ? st->rz : st->rz_new;
@@ -851,7 +874,11 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   const int64_t n = n_nodes * d;
   if (work_bytes < fea_pcg_workspace(n)) return FEA_ERR_WORKSPACE;
   PcgWork w = carve_pcg(work, n);
-  const TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_nodes);
+  TmaPlan plan = tma_plan(d, max_coupled, values, node_colidx, n_nodes, /*small_problem=*/n < kSingleReductionBelowDof);
+  // programmatic dependent launch between the kernels of an iteration (common.cuh); FEA_PCG_PDL=0 switches it off
+  const char* pdl_env = std::getenv("FEA_PCG_PDL");
+  const bool pdl = pdl_env == nullptr || pdl_env[0] != '0';
+  plan.pdl = pdl;
 
   // two pinned snapshots of the state, polled one chunk behind the GPU
   PcgState* snap = static_cast<PcgState*>(pinned_scratch(0, 2 * sizeof(PcgState)));
@@ -906,12 +933,15 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     const int r = pcg_step_spmv(d, n_nodes, node_rowptr, node_colidx, values, w.p, w.ap, 0, w.state, w.partials, stream,
                             &plan);
     if (sample) cudaEventRecord(sample_ev[2 * n_samples++ + 1], stream);
+    const PeerView* no_peer = nullptr;
     if (algo == 1) {
-      pcg_cgcg_kernel<<<cgcg_blocks(n), 256, 0, stream>>>(n, dinv, w.p, w.ap, w.p2, w.s, x, w.r, w.state, w.partials,
-                                                          history, nullptr, PeerKey{});
+      launch_kernel(pcg_cgcg_kernel, dim3(cgcg_blocks(n)), dim3(256), 0, stream, pdl, n, dinv, w.p, w.ap, w.p2, w.s, x, w.r,
+                    w.state, w.partials, history, no_peer, PeerKey{});
     } else {
-      pcg_update_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.p, w.ap, x, w.r, w.state, w.partials, nullptr, PeerKey{});
-      pcg_direction_kernel<<<vb, 256, 0, stream>>>(n, dinv, w.r, w.p, w.state, history, nullptr, PeerKey{});
+      launch_kernel(pcg_update_kernel, dim3(vb), dim3(256), 0, stream, pdl, n, dinv, w.p, w.ap, x, w.r, w.state,
+                    w.partials, no_peer, PeerKey{});
+      launch_kernel(pcg_direction_kernel, dim3(vb), dim3(256), 0, stream, pdl, n, dinv, w.r, w.p, w.state, history,
+                    no_peer, PeerKey{});
     }
     return r;
   };

@@ -89,6 +89,20 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   return policy;
 }
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+__device__ __forceinline__ uint64_t l2_evict_normal_policy() {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+// The kernels' `stages` argument carries the L2 hint of the matrix stream in bits 16..17:
+// 0 evict-first (matrix larger than L2: keep L2 for the vector), 1 normal, 2 evict-last (matrix fits in L2 and is
+// re-read every iteration of a solve: BASELINE config 3, 85 MB).
+constexpr int kTmaHintShift = 16;
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
                                          uint64_t policy) {
   asm volatile(
@@ -214,10 +228,11 @@ template <int D, int G, bool DOT, bool GATED = false>
 __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __restrict__ node_rowptr,
                                               const int32_t* __restrict__ node_colidx,
                                               const double* __restrict__ values, const double* x,
-                                              double* __restrict__ y, const double* x_own, int stages,
+                                              double* __restrict__ y, const double* x_own, int stages_arg,
                                               int val_cap, int col_cap, unsigned char* smem, double& dot,
                                               const HaloGate& gate = HaloGate{}) {
   constexpr int DD = D * D;
+  const int stages = stages_arg & ((1 << kTmaHintShift) - 1), l2_hint = stages_arg >> kTmaHintShift;
   constexpr int ROWS = D * kTileNodes;  // rows per tile
   constexpr int ITEMS = tma_items(D);   // (row, b) pairs per tile
   constexpr int GW = tma_group_warps(D);
@@ -261,7 +276,8 @@ __device__ __forceinline__ void spmv_tma_body(int n_nodes, const int32_t* __rest
         a1 = node_rowptr[n0 + kTileNodes < n_nodes ? n0 + kTileNodes : n_nodes];
       }
     };
-    const uint64_t policy = l2_evict_first_policy();
+    const uint64_t policy = l2_hint == 0 ? l2_evict_first_policy()
+                                         : (l2_hint == 1 ? l2_evict_normal_policy() : l2_evict_last_policy());
     int nxt_r0, nxt_r1;
     fetch(lane, nxt_r0, nxt_r1);
     for (int q0 = 0; blockIdx.x + (int64_t)stride * q0 < n_tiles; q0 += 32) {
@@ -415,8 +431,13 @@ struct TmaPlan {
   TmaLayout layout;
   int max_grid;  // SMs x target CTAs per SM, capped by the number of tiles
   int groups;    // consumer groups per CTA: 1 .. 4
+  int l2_hint = 0;   // see kTmaHintShift
+  bool pdl = false;  // launch with programmatic stream serialisation (fea_pcg_solve's private stream / graph)
 };
 
-TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_colidx, int64_t n_nodes);
+// `small_problem`: the caller will sweep this matrix many times and it is small (fea_pcg_solve below the
+// single-reduction threshold): 3 consumer groups x 3 stages, 2 CTAs per SM instead of 2 x 2, 3 per SM.
+TmaPlan tma_plan(int d, int max_coupled, const void* values, const void* node_colidx, int64_t n_nodes,
+                 bool small_problem = false);
 
 }  // namespace fea

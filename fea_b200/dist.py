@@ -192,6 +192,7 @@ class DistInfo:
     status: int
     bnorm: float
     history: np.ndarray | None = None
+    seconds: float = 0.0  # wall time of the solver proper (synchronised), where the driver measures it
 
 
 def distributed_pcg(ops, plan: SlabPlan, d: int, b_owned: torch.Tensor, dinv_owned: torch.Tensor, tol: float = 1e-12,
@@ -764,7 +765,13 @@ def solve_truss_multi(nodes, members, k, constraints, loads, tol: float = 1e-12,
     B_owned = core.to_device(np.ascontiguousarray(loads[3 * plan.own_lo:3 * plan.own_hi]), torch.float64)
     if max_iter is None:
         max_iter = min(10 * 3 * n_nodes, 2**31 - 1)
+    if nodes_d.is_cuda:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
     X, info = distributed_pcg_multi(K, plan, B_owned, dinv_owned, tol=tol, max_iter=max_iter, group=group)
+    if nodes_d.is_cuda:
+        torch.cuda.synchronize()
+    info.seconds = time.perf_counter() - t0
     if info.status != _lib.FEA_OK:
         _lib.raise_for_status(np.array([info.status, 0x7FFFFFFF - info.iterations]))
     if not gather:

@@ -163,6 +163,9 @@ def config5_dist(n=93, n_rhs=64):
                           "seconds_slice_assemble_solve": t1 - t0, "pcg_iterations": info.iterations,
                           "iterations_per_column_max": int(info.history.max()), "status": info.status,
                           "rel_residual_worst": info.rel_residual, "ms_per_iteration": (t1 - t0) / info.iterations * 1e3,
+                          "seconds_solver_only": info.seconds,
+                          "ms_per_iteration_solver_only": info.seconds / info.iterations * 1e3,
+                          "graph": os.environ.get("FEA_MULTI_GRAPH", "1") != "0",
                           "solved_dof_columns_per_s": free * n_rhs / (t1 - t0),
                           "solver": "distributed_pcg_multi (step kernels of fea_pcg_solve_multi + NCCL halo send/recv "
                                     "and per-column all-reduces)"}))
@@ -180,6 +183,10 @@ if __name__ == "__main__":
     if "2" in which:
         config2()
     if "3" in which:
-        config3()
+        if "--c3" in sys.argv:  # other sizes of the same case: --c3 A b
+            i = sys.argv.index("--c3")
+            config3(int(sys.argv[i + 1]), int(sys.argv[i + 2]))
+        else:
+            config3()
     if "5" in which:
         config5(n_lat)
