@@ -24,6 +24,7 @@
 #include <mutex>
 
 #include "pcg_common.cuh"
+#include "pcg_fused.cuh"
 
 namespace fea {
 
@@ -864,6 +865,45 @@ extern "C" int fea_pcg_step_direction(int64_t n_dof, const double* dinv, const d
   return check_launch();
 }
 
+// One launch of the persistent solver (pcg_fused.cuh): `args.iters` iterations of the single-reduction recurrence.
+template <int D, int G>
+static int launch_fused(const TmaPlan& plan, FusedArgs args, cudaStream_t stream) {
+  static GridCache cache;
+  int grid = 0;
+  FEA_TRY(tma_grid(cache, pcg_fused_kernel<D, G>, plan, tma_threads(D, G), &grid));
+  if (5 * grid > 2 * kMaxPartials) return FEA_ERR_INVALID;
+  FEA_TRY(check(cudaMemsetAsync(&args.st->counter[3], 0, sizeof(uint32_t), stream)));  // the grid barrier's ticket
+  void* kargs[] = {&args};
+  return check(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(pcg_fused_kernel<D, G>), dim3(grid),
+                                           dim3(tma_threads(D, G)), kargs, plan.layout.smem_bytes, stream));
+}
+template <int D>
+static int launch_fused_g(const TmaPlan& plan, const FusedArgs& args, cudaStream_t stream) {
+  switch (plan.groups) {
+    case 1: return launch_fused<D, 1>(plan, args, stream);
+    case 2: return launch_fused<D, 2>(plan, args, stream);
+    case 3: return launch_fused<D, 3>(plan, args, stream);
+    case 4: return launch_fused<D, 4>(plan, args, stream);
+    default: return FEA_ERR_INVALID;
+  }
+}
+static int dispatch_fused(int d, const TmaPlan& plan, const FusedArgs& args, cudaStream_t stream) {
+  switch (d) {
+    case 1: return launch_fused_g<1>(plan, args, stream);
+    case 2: return launch_fused_g<2>(plan, args, stream);
+    case 3: return launch_fused_g<3>(plan, args, stream);
+    default: return FEA_ERR_INVALID;
+  }
+}
+// The persistent kernel needs every CTA resident at once (grid barrier): cooperative launch.
+static bool fused_supported() {
+  int dev = 0, coop = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) return false;
+  const char* env = std::getenv("FEA_PCG_FUSED");
+  return coop != 0 && !(env != nullptr && env[0] == '0');
+}
+
 extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_rowptr, const int32_t* node_colidx,
                              const double* values, int32_t max_coupled, const double* dinv, const double* b,
                              double* x, double tol, int32_t max_iter, void* work, size_t work_bytes,
@@ -911,6 +951,28 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   const unsigned vb = vec_blocks(n);
   const int chunk = 32;
   const int algo = pcg_algorithm(n, false);
+  // L2-sized problems on the single-reduction recurrence: one persistent kernel per chunk of iterations
+  const bool fused = algo == 1 && plan.ok && n_nodes < (int64_t)INT32_MAX / 4 && fused_supported();
+  FusedArgs fargs{};
+  if (fused) {
+    fargs.n_nodes = (int)n_nodes;
+    fargs.node_rowptr = node_rowptr;
+    fargs.node_colidx = node_colidx;
+    fargs.values = values;
+    fargs.dinv = dinv;
+    fargs.u = w.p;
+    fargs.w = w.ap;
+    fargs.p = w.p2;
+    fargs.s = w.s;
+    fargs.x = x;
+    fargs.r = w.r;
+    fargs.stages_arg = plan.layout.stages | (plan.l2_hint << kTmaHintShift);
+    fargs.val_cap = plan.layout.val_cap;
+    fargs.col_cap = plan.layout.col_cap;
+    fargs.st = w.state;
+    fargs.partials = w.partials;
+    fargs.history = history;
+  }
   const int per_iter = algo == 1 ? 2 : 3;  // kernels per iteration
   // the single-reduction variant learns about convergence / max_iter one step later
   const int64_t enqueue_limit = (int64_t)max_iter + (algo == 1 ? 1 : 0);
@@ -949,7 +1011,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   // CUDA-graph launch: the kernel arguments never change, and small problems (100x20x20: ~35 us
   // of kernels per iteration) are otherwise bound by the host's launch rate.
   cudaGraphExec_t graph_exec = nullptr;
-  if (own != nullptr && rc == FEA_OK && max_iter >= chunk) {
+  if (own != nullptr && rc == FEA_OK && max_iter >= chunk && !fused) {
     enqueue_iteration(false);  // warm: every cudaFuncSetAttribute / occupancy query happens outside capture
     rc = check_launch(per_iter);
     enqueued += 1;
@@ -964,15 +1026,19 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     cudaGetLastError();  // a failed capture falls back to plain launches
   }
   while (rc == FEA_OK && !finished) {
-    const int todo = (int)std::min<int64_t>(chunk, enqueue_limit - enqueued);
-    if (graph_exec != nullptr && todo == chunk) {
+    const int todo = (int)std::min<int64_t>(fused ? 4 * chunk : chunk, enqueue_limit - enqueued);
+    if (fused) {
+      fargs.iters = todo;
+      rc = dispatch_fused(d, plan, fargs, stream);
+      if (rc == FEA_OK) profile().launches += 1;
+    } else if (graph_exec != nullptr && todo == chunk) {
       rc = enqueue_iteration(sample_ev != nullptr && n_samples < kMaxSamples);
       if (rc == FEA_OK) rc = check(cudaGraphLaunch(graph_exec, stream));
     } else {
       for (int it = 0; it < todo && rc == FEA_OK; ++it)
         rc = enqueue_iteration(sample_ev != nullptr && it == 0 && n_samples < kMaxSamples);
     }
-    if (rc == FEA_OK) rc = check_launch(per_iter * todo);
+    if (rc == FEA_OK && !fused) rc = check_launch(per_iter * todo);
     if (rc != FEA_OK) break;
     enqueued += todo;
     rc = check(cudaMemcpyAsync(&snap[slot], w.state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
