@@ -19,7 +19,8 @@
 // The grid barrier is a ticket counter in the solver state polled by one thread per CTA (bounded: a CTA that
 // waits ~2 s gives up and the solve ends with FEA_ERR_CUDA instead of hanging the device).  The state block
 // (PcgState) has the same meaning as in the two-kernel path at every launch boundary, so the host loop, the
-// snapshots and the result are shared.  When the solve ends inside a chunk the consumers leave at once; the producer
+// snapshots and the result are shared.  (Exchanging the partials as tagged words polled by every CTA -- barrier and
+// reduction in one, as between GPUs -- was measured too: 27.6 us per iteration against 21.2, 87 k pollers on L2.)  When the solve ends inside a chunk the consumers leave at once; the producer
 // sees their flag, waits for the copies it has already issued to land, and leaves too.
 #pragma once
 #include "pcg_common.cuh"
@@ -232,9 +233,6 @@ __device__ __noinline__ double fused_sweep(int n_nodes, const int32_t* __restric
 
 template <int D, int G>
 __global__ void __launch_bounds__(tma_threads(D, G), tma_min_blocks(D, G)) pcg_fused_kernel(FusedArgs a) {
-  constexpr int DD = D * D;
-  constexpr int ROWS = D * kTileNodes;
-  constexpr int ITEMS = tma_items(D);
   constexpr int GW = tma_group_warps(D);
   constexpr int NW = G * GW;     // consumer warps
   constexpr int CT = NW * 32;    // consumer threads
@@ -247,7 +245,6 @@ __global__ void __launch_bounds__(tma_threads(D, G), tma_min_blocks(D, G)) pcg_f
   const int stages = a.stages_arg & ((1 << kTmaHintShift) - 1), l2_hint = a.stages_arg >> kTmaHintShift;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kTmaMaxStages;
-  double* parts = reinterpret_cast<double*>(smem + kTmaBarrierBytes);  // [2][G][ITEMS]
   unsigned char* stage0 = smem + tma_fixed_bytes(D, G);
   const int val_cap = a.val_cap, col_cap = a.col_cap;
   const int stage_bytes = (int)(sizeof(double) * val_cap + sizeof(int32_t) * col_cap);

@@ -335,6 +335,50 @@ def test_pcg_single_reduction_variant(mods, monkeypatch):
     assert rel(u_api.ravel(), ud.ravel()) < U_RTOL
 
 
+def test_pcg_persistent_kernel_vs_two_kernel_path(mods, monkeypatch):
+    """Below 3 M DOF fea_pcg_solve runs the single-reduction recurrence in ONE persistent kernel per 128
+    iterations (pcg_fused.cuh: grid barriers, every CTA reduces the partial sums itself).  Against the
+    two-kernel path (FEA_PCG_FUSED=0) on the same matrix: same recurrence, another order of the partial sums
+    -> solution 1e-10, crossing of 1e-8 within 2 % of the iterations, history of the first 100 iterations 1e-6; iteration caps on
+    and around a launch boundary; residual history across launches."""
+    core = mods["core"]
+    nodes, elements, cons, forces = fo.cantilever_case(30, 6)
+    rng = np.random.default_rng(5)
+    h = 0.1 / 6
+    nodes = nodes + rng.uniform(-0.15 * h, 0.15 * h, nodes.shape) * (nodes[:, 2:3] > 0)
+    forces = forces + 0.1 * np.abs(forces).max() * rng.standard_normal(forces.shape)
+    nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
+    K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, fixed=core._fixed_mask(cons, nodes.size))
+    b = core.to_device(forces, torch.float64).reshape(-1)
+    monkeypatch.setenv("FEA_PCG_ALGO", "1")
+    monkeypatch.setenv("FEA_PCG_FUSED", "0")
+    u0, i0 = core.pcg(K, b, tol=1e-12, history=True)
+    monkeypatch.setenv("FEA_PCG_FUSED", "1")
+    u1, i1 = core.pcg(K, b, tol=1e-12, history=True)
+    assert i0.status == 0 and i1.status == 0 and i1.rel_residual <= 1e-12
+    assert i0.iterations > 300  # several launches of the persistent kernel
+    # the recurrence residual creeps under 1e-12 at the end (slope ~5 % per iteration): where exactly it crosses
+    # depends on the rounding of the dot products; the crossing of 1e-8 is sharp
+    first_below = lambda hist: int(np.argmax(np.asarray(hist) < 1e-8))
+    assert abs(first_below(i1.history) - first_below(i0.history)) <= max(3, first_below(i0.history) // 50)
+    assert abs(i1.iterations - i0.iterations) <= i0.iterations // 6
+    assert rel(u1.cpu().numpy(), u0.cpu().numpy()) < 1e-10
+    k = min(100, len(i0.history), len(i1.history))
+    assert np.allclose(i1.history[:k], i0.history[:k], rtol=1e-6)
+    assert len(i1.history) == i1.iterations and abs(i1.history[-1] - i1.rel_residual) < 1e-15
+    # across the launch boundary at 128 (by iteration 200 the two roundings have drifted 1 % apart on this case)
+    assert np.allclose(i1.history[100:140], i0.history[100:140], rtol=1e-4)
+    u1b, i1b = core.pcg(K, b, tol=1e-12)
+    assert torch.equal(u1, u1b) and i1b.iterations == i1.iterations  # deterministic
+    for cap in (1, 64, 127, 128, 129):  # (later the two roundings of this case drift apart: 1 % by iteration 200)
+        monkeypatch.setenv("FEA_PCG_FUSED", "1")
+        uc, ic = core.pcg(K, b, tol=1e-12, max_iter=cap, raise_on_failure=False)
+        monkeypatch.setenv("FEA_PCG_FUSED", "0")
+        ud, idd = core.pcg(K, b, tol=1e-12, max_iter=cap, raise_on_failure=False)
+        assert ic.iterations == cap == idd.iterations and ic.status == idd.status != 0
+        assert rel(uc.cpu().numpy(), ud.cpu().numpy()) < (1e-9 if cap <= 64 else 1e-5)
+
+
 def test_pcg_zero_rhs_and_singular(mods):
     core = mods["core"]
     nodes, elements, cons, forces = fo.cantilever_case(3, 2)
@@ -906,7 +950,7 @@ def test_config5_full_size_properties(mods):
     assert info.iterations == 48 and float(rel_res.max()) < 0.5  # every column is converging
 
 
-def test_p2p_solver_single_rank(mods):
+def test_p2p_solver_single_rank(mods, monkeypatch):
     """fea_pcg_solve_p2p with world = 1 (no peers): exercises the comm block API, the private
     stream / CUDA-graph driver and the p-in-comm-block layout on one GPU; must reproduce
     fea_pcg_solve bit for bit (same kernels, same order)."""
@@ -916,6 +960,10 @@ def test_p2p_solver_single_rank(mods):
 
     core = mods["core"]
     lib = _lib.load()
+    # "same kernels": the two-kernel path with the pipeline shape the peer-memory solver uses (below 3 M DOF
+    # fea_pcg_solve would otherwise take the persistent kernel on a 3-group pipeline)
+    monkeypatch.setenv("FEA_PCG_FUSED", "0")
+    monkeypatch.setenv("FEA_TMA_CFG", "2,2,3")
     nodes, elements, cons, forces = fo.cantilever_case(24, 5)
     nd, el = core.to_device(nodes, torch.float64), core.to_device(elements, torch.int32)
     K = core.assemble_hex8(nd, el, fo.E_HEX, fo.NU_HEX, fixed=core._fixed_mask(cons, nodes.size))
