@@ -108,27 +108,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // All consumer threads of all CTAs.  Returns false when the other CTAs never arrived.
+// One thread per CTA: release fence, ticket, RELAXED polls, one acquire fence at the end (MEMBAR.ALL.GPU +
+// CCTL.IVALL: the invalidation of this SM's L1 that the ordinary loads of u and w rely on).  An acquire load per poll
+// (LDG.STRONG.GPU + CCTL.IVALL each time) would keep wiping the L1 under the other CTA of the SM while it still sweeps.
 __device__ __forceinline__ bool fused_grid_barrier(unsigned* counter, unsigned target, int ctid, int nthreads,
                                                    int* s_fail) {
   group_barrier(kFusedBarrierId, nthreads);
   if (ctid == 0) {
-    __threadfence();
+    fence_acq_rel_gpu();
     atomicAdd(counter, 1u);
     int polls = 0;
-    while (ld_acquire_gpu_u32(counter) < target) {
+    while (ld_relaxed_gpu_u32(counter) < target) {
       if (++polls > (1 << 24)) {
         *s_fail = 1;
         break;
       }
     }
-    __threadfence();
+    fence_acq_rel_gpu();
   }
   group_barrier(kFusedBarrierId, nthreads);
   return *s_fail == 0;
