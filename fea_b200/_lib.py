@@ -102,6 +102,9 @@ PROTOTYPES = {
     "fea_comm_ipc_export": (c_int32, [P, P]),
     "fea_comm_ipc_open": (c_int32, [P, ctypes.POINTER(c_void_p)]),
     "fea_comm_ipc_close": (c_int32, [P]),
+    "fea_peer_push": (c_int32, [P, P, P, P, c_int64, P, P, P, c_int64, P, c_int64, P]),
+    "fea_peer_wait": (c_int32, [P, c_int32, c_int32, P, c_int64, P]),
+    "fea_comm_error": (c_int32, [P, P, P]),
     "fea_pcg_solve_p2p": (c_int32, [c_int64, c_int32, P, P, P, c_int32, P, P, P, c_double, c_int32, P, c_size_t, P,
                                     ctypes.POINTER(PeerComm), ctypes.POINTER(PcgResult), P]),
     "fea_chain_solve_workspace": (c_size_t, [c_int64, c_int32, c_int32]),

@@ -113,9 +113,86 @@ __global__ void __launch_bounds__(kHaloThreads, 10) p2p_halo_kernel(PeerView pv,
   dbg_stamp(own, st->iter, 4);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stand-alone halo exchange (fea_peer_push / fea_peer_wait): the many-load-case solver on slabs moves
+// (rows x 64) search directions, 13 MB per neighbour and iteration at BASELINE config 5.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPushThreads = 256;
+__global__ void __launch_bounds__(kPushThreads)
+peer_push_kernel(CommHeader* own, CommHeader* lower, const double2* __restrict__ src_lower, double2* dst_lower,
+                 long long n2_lower, CommHeader* upper, const double2* __restrict__ src_upper, double2* dst_upper,
+                 long long n2_upper, const int32_t* iter, long long epoch) {
+  __shared__ bool s_last;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lower != nullptr)
+    for (long long i = tid; i < n2_lower; i += stride) dst_lower[i] = src_lower[i];
+  if (upper != nullptr)
+    for (long long i = tid; i < n2_upper; i += stride) dst_upper[i] = src_upper[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&own->counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  own->counter = 0;
+  __threadfence_system();
+  const long long tag = (epoch << 32) | ((long long)*iter + 1);
+  if (lower != nullptr) st_release_sys(&lower->halo_tag[1], tag);  // I am its upper neighbour
+  if (upper != nullptr) st_release_sys(&upper->halo_tag[0], tag);
+}
+
+__global__ void peer_wait_kernel(CommHeader* own, int has_lower, int has_upper, const int32_t* iter, long long epoch) {
+  const long long want = (epoch << 32) | ((long long)*iter + 1);
+  bool ok = true;
+  if (has_lower) ok = spin_until(&own->halo_tag[0], want, true) && ok;
+  if (has_upper) ok = spin_until(&own->halo_tag[1], want, true) && ok;
+  if (!ok) own->error = 1;
+}
+
 }  // namespace fea
 
 using namespace fea;
+
+extern "C" int fea_peer_push(void* own_block, void* lower_block, const double* src_lower, double* dst_lower,
+                             int64_t count_lower, void* upper_block, const double* src_upper, double* dst_upper,
+                             int64_t count_upper, const int32_t* iter_dev, int64_t epoch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!own_block || !iter_dev || count_lower < 0 || count_upper < 0) return FEA_ERR_INVALID;
+  const bool lo = lower_block != nullptr && count_lower > 0, hi = upper_block != nullptr && count_upper > 0;
+  if (lo && (!src_lower || !dst_lower || (count_lower & 1) || ((uintptr_t)src_lower & 15) || ((uintptr_t)dst_lower & 15)))
+    return FEA_ERR_INVALID;
+  if (hi && (!src_upper || !dst_upper || (count_upper & 1) || ((uintptr_t)src_upper & 15) || ((uintptr_t)dst_upper & 15)))
+    return FEA_ERR_INVALID;
+  if (!lo && !hi) return FEA_OK;
+  const int64_t n2 = std::max<int64_t>(lo ? count_lower / 2 : 0, hi ? count_upper / 2 : 0);
+  const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n2, kPushThreads * 4), 296));
+  peer_push_kernel<<<blocks, kPushThreads, 0, stream>>>(
+      static_cast<CommHeader*>(own_block), lo ? static_cast<CommHeader*>(lower_block) : nullptr,
+      reinterpret_cast<const double2*>(src_lower), reinterpret_cast<double2*>(dst_lower), count_lower / 2,
+      hi ? static_cast<CommHeader*>(upper_block) : nullptr, reinterpret_cast<const double2*>(src_upper),
+      reinterpret_cast<double2*>(dst_upper), count_upper / 2, iter_dev, (long long)epoch);
+  return check_launch();
+}
+
+extern "C" int fea_peer_wait(void* own_block, int32_t has_lower, int32_t has_upper, const int32_t* iter_dev,
+                             int64_t epoch, void* stream_) {
+  if (!own_block || !iter_dev) return FEA_ERR_INVALID;
+  if (!has_lower && !has_upper) return FEA_OK;
+  peer_wait_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<CommHeader*>(own_block), has_lower,
+                                                                   has_upper, iter_dev, (long long)epoch);
+  return check_launch();
+}
+
+extern "C" int fea_comm_error(void* own_block, int32_t* error_host, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!own_block || !error_host) return FEA_ERR_INVALID;
+  int err = 0;
+  FEA_TRY(check(cudaMemcpyAsync(&err, &static_cast<CommHeader*>(own_block)->error, sizeof(int), cudaMemcpyDeviceToHost,
+                                stream)));
+  FEA_TRY(check(cudaStreamSynchronize(stream)));
+  *error_host = err;
+  return FEA_OK;
+}
 
 extern "C" size_t fea_comm_bytes(int64_t n_local_dof) {
   return kCommHeaderBytes + align_up(sizeof(double) * (size_t)n_local_dof, 256);

@@ -152,6 +152,18 @@ def plan_slab(elements: np.ndarray, cuts: np.ndarray, rank: int) -> SlabPlan:
 # ------------------------------------------------------------------------------------------------
 # halo exchange + distributed PCG driver (backend-agnostic)
 # ------------------------------------------------------------------------------------------------
+class _DeviceMemory:
+    """Raw device memory as a __cuda_array_interface__ provider (zero-copy torch view)."""
+
+    def __init__(self, ptr: int, n_doubles: int):
+        self.__cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _device_view(ptr: int, n_doubles: int, device) -> torch.Tensor:
+    return torch.as_tensor(_DeviceMemory(ptr, n_doubles), device=device)
+
+
 class HaloExchange:
     """Grouped send/recv of the boundary node values of a local vector (d values per node)."""
 
@@ -664,8 +676,24 @@ def distributed_pcg_multi(K, plan: SlabPlan, B_owned: torch.Tensor, dinv_owned: 
     dev = B_owned.device
     B_owned = B_owned.contiguous()
     X = torch.empty_like(B_owned)
-    P_ext = torch.zeros((plan.n_local * d, R), dtype=torch.float64, device=dev)
+    multi = plan.world > 1
+    # Halo exchange: NVLink peer memory when it can be set up (the search directions then live in this rank's
+    # IPC-shared communication block and the neighbours store their face rows straight into it:
+    # fea_peer_push / fea_peer_wait), else grouped NCCL / gloo send / recv.  FEA_DIST_COMM=nccl forces the latter.
+    peer = None
+    if (multi and dev.type == "cuda" and dist.get_backend(group) == "nccl"
+            and os.environ.get("FEA_DIST_COMM", "p2p") != "nccl"):
+        comm = P2PComm.get(plan, d * R, group)
+        if comm.available:
+            peer = comm
+    if peer is not None:
+        header = int(lib.fea_comm_bytes(0))
+        P_ext = _device_view(peer.own + header, plan.n_local * d * R, dev).view(plan.n_local * d, R)
+        P_ext.zero_()
+    else:
+        P_ext = torch.zeros((plan.n_local * d, R), dtype=torch.float64, device=dev)
     P_own = P_ext[plan.offset * d:plan.offset * d + n_own]
+    SOLVER_USED["multi_halo"] = "p2p" if peer is not None else ("nccl" if multi else "none")
     ws_bytes = lib.fea_pcg_multi_workspace(n_own, R)
     work = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     off = (ctypes.c_int64 * 5)()
@@ -681,9 +709,30 @@ def distributed_pcg_multi(K, plan: SlabPlan, B_owned: torch.Tensor, dinv_owned: 
     iters = work[off[3]:off[3] + 4 * R].view(torch.int32)
     pt = K.pattern
     rowptr_owned = pt.node_rowptr[plan.offset:]
-    halo = HaloExchange(plan, d, group)
-    multi = plan.world > 1
     s = core._stream
+    if peer is not None:
+        peer.epoch += 1
+        epoch, row_bytes = peer.epoch, 8 * d * R
+        lower_block = upper_block = src_lo = dst_lo = src_hi = dst_hi = None
+        cnt_lo = cnt_hi = 0
+        if plan.send_down is not None:
+            r, lo, hi = plan.send_down
+            lower_block, cnt_lo = peer.ptrs[r], (hi - lo) * d * R
+            src_lo = P_ext.data_ptr() + (lo - plan.g_lo) * row_bytes
+            dst_lo = peer.ptrs[r] + header + (lo - peer.g_los[r]) * row_bytes
+        if plan.send_up is not None:
+            r, lo, hi = plan.send_up
+            upper_block, cnt_hi = peer.ptrs[r], (hi - lo) * d * R
+            src_hi = P_ext.data_ptr() + (lo - plan.g_lo) * row_bytes
+            dst_hi = peer.ptrs[r] + header + (lo - peer.g_los[r]) * row_bytes
+        has_lo, has_hi = int(plan.recv_down is not None), int(plan.recv_up is not None)
+
+        def halo(_vec) -> None:
+            _lib.check(lib.fea_peer_push(peer.own, lower_block, src_lo, dst_lo, cnt_lo, upper_block, src_hi, dst_hi,
+                                         cnt_hi, state.data_ptr(), epoch, s()), "fea_peer_push")
+            _lib.check(lib.fea_peer_wait(peer.own, has_lo, has_hi, state.data_ptr(), epoch, s()), "fea_peer_wait")
+    else:
+        halo = HaloExchange(plan, d, group)
     _lib.check(lib.fea_pcg_multi_init(n_own, R, B_owned.data_ptr(), dinv_owned.data_ptr(), X.data_ptr(),
                                       P_own.data_ptr(), float(tol), int(max_iter), work.data_ptr(), ws_bytes, s()),
                "fea_pcg_multi_init")
@@ -727,6 +776,11 @@ def distributed_pcg_multi(K, plan: SlabPlan, B_owned: torch.Tensor, dinv_owned: 
             done_iter += todo
         st = state.cpu()  # one synchronisation per chunk; the decisions are identical on every rank
         finished = bool(int(st[1]) != 0) or done_iter >= max_iter
+    if peer is not None:
+        err = ctypes.c_int32(0)
+        _lib.check(lib.fea_comm_error(peer.own, ctypes.byref(err), s()), "fea_comm_error")
+        if err.value != 0:
+            _lib.raise_for_status(np.array([_lib.FEA_ERR_PEER, 0x7FFFFFFF]))
     st = state.cpu()
     sc = scal.cpu().numpy()
     bn2, rr = sc[R:2 * R], sc[3 * R:4 * R]

@@ -271,6 +271,26 @@ int fea_comm_ipc_export(void* ptr, unsigned char* handle64_host);
 int fea_comm_ipc_open(const unsigned char* handle64_host, void** out);
 int fea_comm_ipc_close(void* ptr);
 
+/* Stand-alone halo exchange over the same blocks, for solvers driven from the host side (the many-load-case
+ * PCG on slabs, BASELINE config 5: fea_b200/dist.py distributed_pcg_multi).  Replaces a pair of NCCL
+ * send / recv per neighbour and iteration.
+ * fea_peer_push: copy `count_*` doubles (multiples of 2, 16-byte aligned) from this rank's vector into the
+ *   neighbours' vectors (peer pointers from fea_comm_ipc_open), one system-scope fence, then the tag
+ *   (epoch << 32 | *iter_dev + 1) into the neighbours' headers.  A null destination skips that side.
+ * fea_peer_wait: hold the stream until both neighbours' tags for (epoch, *iter_dev + 1) have arrived in this
+ *   rank's header (bounded, ~2 s: then the header's error word is set and fea_comm_error returns it).
+ * `own_block` / `lower_block` / `upper_block` are block base pointers (header first); `iter_dev` is the
+ * solver's device-resident iteration counter, so both calls can sit in a replayed CUDA graph.
+ * Reuse of the halo rows needs no second handshake when a world-wide reduction separates the reader's SpMM
+ * from the next push, as in PCG. */
+int fea_peer_push(void* own_block, void* lower_block, const double* src_lower, double* dst_lower, int64_t count_lower,
+                  void* upper_block, const double* src_upper, double* dst_upper, int64_t count_upper,
+                  const int32_t* iter_dev, int64_t epoch, void* stream);
+int fea_peer_wait(void* own_block, int32_t has_lower, int32_t has_upper, const int32_t* iter_dev, int64_t epoch,
+                  void* stream);
+/* error word of a block's header (device -> host copy, synchronises `stream`): 0, or 1 after a timed-out wait */
+int fea_comm_error(void* own_block, int32_t* error_host, void* stream);
+
 /* Arguments as fea_pcg_solve, restricted to this rank's owned rows: node_rowptr_owned points at
  * the first owned node's entry of the slab's node_rowptr (entries stay absolute), dinv / b / x have
  * n_owned_nodes * dof_per_node entries.  history as in fea_pcg_solve (every rank records the same

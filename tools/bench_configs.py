@@ -167,8 +167,9 @@ def config5_dist(n=93, n_rhs=64):
                           "ms_per_iteration_solver_only": info.seconds / info.iterations * 1e3,
                           "graph": os.environ.get("FEA_MULTI_GRAPH", "1") != "0",
                           "solved_dof_columns_per_s": free * n_rhs / (t1 - t0),
-                          "solver": "distributed_pcg_multi (step kernels of fea_pcg_solve_multi + NCCL halo send/recv "
-                                    "and per-column all-reduces)"}))
+                          "halo_exchange": fdist.SOLVER_USED.get("multi_halo"),
+                          "solver": "distributed_pcg_multi (step kernels of fea_pcg_solve_multi, halo rows over NVLink peer "
+                                    "memory [p2p] or NCCL send/recv [nccl], per-column NCCL all-reduces, CUDA-graph chunks)"}))
     dist.barrier()
     dist.destroy_process_group()
 
