@@ -111,6 +111,55 @@ def hex8_ke(nodes8: np.ndarray, E: float, nu: float) -> np.ndarray:
     return Ke
 
 
+def hex8_trilinear_coefficients(nodes8: np.ndarray) -> np.ndarray:
+    """8 x (coefficient vectors of 1, xi, eta, xi.eta, zeta, xi.zeta, eta.zeta, xi.eta.zeta) of the trilinear map
+    x(xi, eta, zeta) = sum_a N_a X_a (utils.py:159-197), i.e. the Walsh-Hadamard transform of the corners over
+    their three sign bits.  Row m (bits: 1 = xi, 2 = eta, 4 = zeta).  Rows 1, 2, 4 are the rows of 8 J at the centre."""
+    X = np.asarray(nodes8, dtype=np.float64)
+    # corner whose (x, y, z) sign bits are the bits of m, then the butterfly bit by bit: differences of corners that
+    # share coordinate values cancel EXACTLY in this order (a plain signed sum over the 8 corners does not), which
+    # is what makes "== 0" a usable test on grid elements
+    c = np.array([X[[a for a in range(8) if tuple(HEX8_SIGNS[a] > 0) == (bool(m & 1), bool(m & 2), bool(m & 4))][0]]
+                  for m in range(8)])
+    for bit in (1, 2, 4):
+        for m in range(8):
+            if not m & bit:
+                lo, hi = c[m].copy(), c[m | bit].copy()
+                c[m], c[m | bit] = lo + hi, hi - lo
+    return c
+
+
+def hex8_ke_affine(nodes8: np.ndarray, E: float, nu: float) -> np.ndarray:
+    """Closed form of `hex8_ke` for an AFFINE element (a parallelepiped: the xi.eta, xi.zeta, eta.zeta and
+    xi.eta.zeta coefficients of the trilinear map vanish, so J is constant).  The 2x2x2 quadrature of
+    utils.py:200-237 then reduces to
+        S_ab = sum_gp detJ grad N_a grad N_b^T = adj(Jc) M_ab adj(Jc)^T / (8 det Jc),   Jc = 8 J,
+        M_ab = sum_gp dN_a dN_b^T  (a constant table),
+    and K_ab[r][r] = C11 S_rr + C44 (S_ss + S_tt), K_ab[r][c] = C12 S_rc + C44 S_cr with the entries of the C of
+    utils.py:144-153.  This is the checker of the CUDA assembly's fast path (fea_b200/csrc/assemble.cu); it must
+    agree with `hex8_ke` to rounding on every affine element."""
+    c = hex8_trilinear_coefficients(nodes8)
+    Jc = np.array([c[1], c[2], c[4]])
+    det = np.linalg.det(Jc)
+    if det <= 0:
+        raise ValueError(JACOBIAN_MESSAGE)
+    adj = np.linalg.inv(Jc) * det
+    dN = [hex8_shape_derivatives(*gp) for gp in gauss_points_2x2x2()]
+    C = elasticity_matrix(E, nu)
+    c11, c12, c44 = C[0, 0], C[0, 1], C[3, 3]
+    Ke = np.zeros((24, 24))
+    for a in range(8):
+        for b in range(8):
+            M = sum(np.outer(d[:, a], d[:, b]) for d in dN)
+            S = adj @ M @ adj.T / (8.0 * det)
+            blk = c12 * S + c44 * S.T
+            tr = np.trace(S)
+            for r in range(3):
+                blk[r, r] = c11 * S[r, r] + c44 * (tr - S[r, r])
+            Ke[3 * a:3 * a + 3, 3 * b:3 * b + 3] = blk
+    return Ke
+
+
 def _det_inv_3x3(J: np.ndarray):
     """Closed-form det / inverse of a stack of 3x3 matrices (what utils.py:211,218 get from
     LAPACK; differs from it by rounding only)."""

@@ -57,6 +57,28 @@ def test_distorted_ke(golden):
         assert rel(fo.hex8_ke(x, E, nu), k) < 1e-14
 
 
+def test_affine_closed_form_ke(golden):
+    """The closed form the CUDA assembly uses on exactly affine elements (oracle.hex8_ke_affine) against the
+    reference-generated Ke of the cube (K1) and against the Gauss-point oracle on sheared parallelepipeds; the
+    trilinear coefficients that decide affinity vanish exactly on grid elements and not on distorted ones."""
+    g = golden("hex8_single.npz")
+    assert rel(fo.hex8_ke_affine(g["cube"], 1000, 0.0), g["ke_cube"]) < 1e-13
+    rng = np.random.default_rng(0)
+    cube = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    for _ in range(5):
+        T = np.eye(3) + 0.3 * rng.standard_normal((3, 3))
+        if np.linalg.det(T) < 0:
+            T[0] *= -1
+        X = cube @ T.T * 0.37 + rng.standard_normal(3)
+        ref = fo.hex8_ke(X, fo.E_HEX, fo.NU_HEX)
+        assert np.abs(fo.hex8_ke_affine(X, fo.E_HEX, fo.NU_HEX) - ref).max() / np.abs(ref).max() < 1e-12
+    nodes, elements, _, _ = fo.cantilever_case(6, 3)
+    for e in elements:
+        assert np.all(fo.hex8_trilinear_coefficients(nodes[e])[[3, 5, 6, 7]] == 0.0)  # exactly affine: grid rows share values
+    tn, te = fo.tube_case()[:2]
+    assert all(np.abs(fo.hex8_trilinear_coefficients(tn[e])[[3, 5, 6, 7]]).max() > 0 for e in te[:50])
+
+
 def test_k4_stack_faces(golden):
     g = golden("stack_faces.npz")
     n, e = fo.stack_faces_2d(np.array([[0.0, 0], [1, 0], [1, 1], [0, 1]]), np.array([[0, 1, 2, 3]]), [0.0, 1.0, 2.0])
