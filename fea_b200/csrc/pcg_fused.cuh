@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(tma_threads(D, G), tma_min_blocks(D, G)) pcg_f
   __shared__ double s_scratch[3 * NW];
   __shared__ int s_fail;
   __shared__ int s_stop;  // consumers -> producer: the solve has ended, issue nothing more
-  __shared__ double s_sc[6];
-  __shared__ int s_iter;  // iterations completed so far
+  __shared__ double s_sc[8];  // [6] ||b||^2  [7] tol^2: constants of the solve
+  __shared__ int s_iter;      // iterations completed so far
+  __shared__ int s_max_iter;
   const int stages = a.stages_arg & ((1 << kTmaHintShift) - 1), l2_hint = a.stages_arg >> kTmaHintShift;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kTmaMaxStages;
@@ -358,7 +359,10 @@ __global__ void __launch_bounds__(tma_threads(D, G), tma_min_blocks(D, G)) pcg_f
     s_sc[3] = st->spare[0];
     s_sc[4] = st->spare[1];
     s_sc[5] = st->spare[2];
+    s_sc[6] = st->bnorm2;
+    s_sc[7] = st->tol2;
     s_iter = it0;
+    s_max_iter = st->max_iter;
   }
   group_barrier(kFusedBarrierId, CT);
   unsigned* counter = &st->counter[3];
@@ -369,6 +373,21 @@ __global__ void __launch_bounds__(tma_threads(D, G), tma_min_blocks(D, G)) pcg_f
     // ---------------------------------------------------------------- phase 1: w = K u, delta = u.w
     const double dot = fused_sweep<D, G>(n_nodes, node_rowptr, node_colidx, values, a.u, a.w, smem, a.stages_arg, val_cap,
                                          col_cap, it, Q, Qr);
+    // The operands of this thread's first vector element that nobody else writes (everything but w) are fetched now:
+    // their L2 latency hides behind the reduction and the grid barrier (whose fence empties L1 every time).
+    const int64_t j0 = e_lo + ctid;
+    const bool own0 = j0 < e_hi;
+    double di0 = 0.0, u0 = 0.0, rv0 = 0.0, xv0 = 0.0, pv0 = 0.0, sv0 = 0.0;
+    if (own0) {
+      di0 = a.dinv[j0];
+      u0 = __ldcg(a.u + j0);
+      rv0 = a.r[j0];
+      xv0 = a.x[j0];
+      if (s_iter != 0) {
+        pv0 = a.p[j0];
+        sv0 = a.s[j0];
+      }
+    }
     {
       double v[1] = {dot};
       consumer_sum<NW, 1>(v, s_scratch, warp, lane, CT);
@@ -386,8 +405,8 @@ __global__ void __launch_bounds__(tma_threads(D, G), tma_min_blocks(D, G)) pcg_f
 
     // ---------------------------------------------------------------- phase 2: scalars, vector update
     const int iter = s_iter;
-    const double bnorm2 = st->bnorm2, tol2 = st->tol2;
-    const int max_iter = st->max_iter;
+    const double bnorm2 = s_sc[6], tol2 = s_sc[7];
+    const int max_iter = s_max_iter;
     double gamma = s_sc[0], rr = s_sc[1];
     const double gamma_old = s_sc[2], alpha_old = s_sc[3], best_rr = s_sc[4], best_it = s_sc[5];
     double delta;
@@ -445,13 +464,7 @@ __global__ void __launch_bounds__(tma_threads(D, G), tma_min_blocks(D, G)) pcg_f
       break;
     }
     double s_ru = 0.0, s_rr = 0.0;
-    for (int64_t j = e_lo + ctid; j < e_hi; j += CT) {
-      const double di = a.dinv[j], uj = __ldcg(a.u + j), wj = __ldcg(a.w + j), rj = a.r[j], xj = a.x[j];
-      double pj = 0.0, sj = 0.0;
-      if (iter != 0) {
-        pj = a.p[j];
-        sj = a.s[j];
-      }
+    auto update = [&](int64_t j, double di, double uj, double wj, double rj, double xj, double pj, double sj) {
       const double pn = iter == 0 ? uj : fma(beta, pj, uj);
       const double sn = iter == 0 ? wj : fma(beta, sj, wj);
       const double rn = fma(-alpha, sn, rj);
@@ -465,6 +478,16 @@ __global__ void __launch_bounds__(tma_threads(D, G), tma_min_blocks(D, G)) pcg_f
         s_ru = fma(rn, un, s_ru);
         s_rr = fma(rn, rn, s_rr);
       }
+    };
+    if (own0) update(j0, di0, u0, __ldcg(a.w + j0), rv0, xv0, pv0, sv0);
+    for (int64_t j = j0 + CT; j < e_hi; j += CT) {
+      const double di = a.dinv[j], uj = __ldcg(a.u + j), wj = __ldcg(a.w + j), rj = a.r[j], xj = a.x[j];
+      double pj = 0.0, sj = 0.0;
+      if (iter != 0) {
+        pj = a.p[j];
+        sj = a.s[j];
+      }
+      update(j, di, uj, wj, rj, xj, pj, sj);
     }
     {
       double v[2] = {s_ru, s_rr};
