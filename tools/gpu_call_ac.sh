@@ -1,6 +1,8 @@
 #!/bin/bash
 # same-box A/B of the multi-GPU kernels (forced on one GPU, the slab of a rank at N = 8): session-start library vs now;
-# then config 3 with the current persistent kernel
+# then config 3 with the current persistent kernel.  The old library is not kept in the tree; rebuild it with
+#   git archive e050de3 fea_b200 include | tar -x -C /tmp/oldsrc && (cd /tmp/oldsrc && python -c "from fea_b200 import build; build.build_library(force=True)")
+#   mkdir -p tools/experiments/_ab && cp /tmp/oldsrc/fea_b200/csrc/libfea_b200.so tools/experiments/_ab/libfea_b200_e050de3.so
 mkdir -p gpurun_out
 OLD=tools/experiments/_ab/libfea_b200_e050de3.so
 for rep in 1 2; do
