@@ -39,13 +39,38 @@ __device__ __forceinline__ double eliminate(double v, const uint8_t* __restrict_
 // then the accumulator (3 x 3cnt doubles, exactly the node's slice of `values`) is stored.
 // ------------------------------------------------------------------------------------------
 constexpr int kAsmWarps = 4;
+constexpr int kGaussDoubles = 10;  // J^-1 (row-major) and detJ of one (element, Gauss point)
 
-__global__ void __launch_bounds__(kAsmWarps * 32, 4)
+// Thread per (element, Gauss point): the half of the geometry that does not depend on the node a block row belongs
+// to.  Round 1 recomputed it in each of the 8 nodes of an element (a third of the Gauss-point kernel's FP64 work).
+__global__ void __launch_bounds__(256)
+hex8_gauss_geometry_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ elements, int64_t n_elem,
+                           double* __restrict__ gauss, int32_t* status) {
+  __shared__ double s_tab[kShapeTable];
+  hex8_fill_shape_table(s_tab);
+  __syncthreads();
+  const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = id >> 3;
+  const int gp = (int)(id & 7);
+  if (e >= n_elem) return;
+  double I[3][3];
+  const double det = hex8_inverse_jacobian(nodes, elements + e * 8, s_tab, gp, I);
+  if (!(det > 0.0)) raise_status(status, FEA_ERR_JACOBIAN, (int)e);
+  double2* out = reinterpret_cast<double2*>(gauss + id * kGaussDoubles);
+  out[0] = make_double2(I[0][0], I[0][1]);
+  out[1] = make_double2(I[0][2], I[1][0]);
+  out[2] = make_double2(I[1][1], I[1][2]);
+  out[3] = make_double2(I[2][0], I[2][1]);
+  out[4] = make_double2(I[2][2], det);
+}
+
+__global__ void __launch_bounds__(kAsmWarps * 32, 5)
 assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ elements, int64_t n_nodes,
                      Hex8Material mat, const int32_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e,
                      const int32_t* __restrict__ node_rowptr, const int32_t* __restrict__ node_colidx, int maxc,
                      const uint8_t* __restrict__ fixed, int mode, double* __restrict__ values,
-                     double* __restrict__ dinv, const uint8_t* __restrict__ todo, int32_t* status) {
+                     double* __restrict__ dinv, const uint8_t* __restrict__ todo, const double* __restrict__ gauss,
+                     int32_t* status) {
   extern __shared__ double s_dyn[];
   // layout: shape table | per warp: grad, detj, acc[9*maxc], cols[maxc] (ints, padded to doubles)
   double* s_tab = s_dyn;
@@ -86,11 +111,14 @@ assemble_hex8_kernel(const double* __restrict__ nodes, const int32_t* __restrict
         e = inc >> 3;
         a_own = inc & 7;
       }
-      if (active) {  // phase A
+      if (active) {  // phase A: J^-1 and detJ come from hex8_gauss_geometry_kernel (once per element), the gradients here
         const int gp = lane & 7;
-        const double det = hex8_geometry(nodes, elements + (int64_t)e * 8, s_tab, gp, t, grad);
-        detj[gp * 4 + t] = det;
-        if (!(det > 0.0)) raise_status(status, FEA_ERR_JACOBIAN, e);
+        const double2* rec = reinterpret_cast<const double2*>(gauss + ((int64_t)e * 8 + gp) * kGaussDoubles);
+        const double2 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3), q4 = __ldg(rec + 4);
+        const double I[3][3] = {{q0.x, q0.y, q1.x}, {q1.y, q2.x, q2.y}, {q3.x, q3.y, q4.x}};
+        hex8_gradients(I, s_tab, gp, t, grad);
+        detj[gp * 4 + t] = q4.y;
+        if (!(q4.y > 0.0)) raise_status(status, FEA_ERR_JACOBIAN, e);
       }
       __syncwarp();
       double blk[3][3];
@@ -166,7 +194,7 @@ constexpr int kGeomDoubles = 10;
 
 __global__ void __launch_bounds__(256)
 hex8_affine_geometry_kernel(const double* __restrict__ nodes, const int32_t* __restrict__ elements, int64_t n_elem,
-                            double* __restrict__ geom, int32_t* status) {
+                            double* __restrict__ geom, unsigned* __restrict__ n_general, int32_t* status) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_elem) return;
   // c[m] = corner whose (x, y, z) sign bits are the bits of m (hex8.cuh: kSignX/Y/Z)
@@ -217,6 +245,10 @@ hex8_affine_geometry_kernel(const double* __restrict__ nodes, const int32_t* __r
 #pragma unroll
   for (int k = 0; k < 9; ++k) out[k] = A[k];
   out[9] = scale;
+  // elements the closed form cannot take (not affine, or inverted): one atomic per warp
+  const unsigned active = __activemask();  // the threads of the warp that have an element (and are here together)
+  const unsigned votes = __ballot_sync(active, !(scale > 0.0));
+  if (votes != 0 && (int)(threadIdx.x & 31) == __ffs(active) - 1) atomicAdd(n_general, (unsigned)__popc(votes));
 }
 
 // Position of `key` in a sorted list padded to 32 entries with INT32_MAX: five loads, no branches.
@@ -531,43 +563,69 @@ extern "C" int fea_assemble_hex8(const double* nodes, const int32_t* elements, i
     FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
   }
   // Pass 0 + 1: nodes whose incident elements are all exactly affine (hex8_affine_geometry_kernel,
-  // assemble_hex8_affine_kernel); a per-node flag is left for the others.  Pass 2: the general kernel on those.
+  // assemble_hex8_affine_kernel); a per-node flag is left for the others and the elements the closed form cannot
+  // take are counted.  If there are any: pass 0b (J^-1 and detJ of every element at its 8 Gauss points, once) and
+  // pass 2 (the Gauss-point kernel on the flagged nodes).  Scratch is stream-ordered memory of the device's default
+  // pool, which keeps what it has handed out once (release threshold): no OS allocation per assembly.
+  int dev = 0;
+  cudaMemPool_t pool = nullptr;
+  FEA_TRY(check(cudaGetDevice(&dev)));
+  FEA_TRY(check(cudaDeviceGetDefaultMemPool(&pool, dev)));
+  uint64_t keep = 1ull << 31;
+  FEA_TRY(check(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)));
   uint8_t* todo = nullptr;
   double* geom = nullptr;
   const size_t smem_aff =
       sizeof(double) * (kMtab + (size_t)kAffWarps * kAffNodes * (9 * (size_t)maxc + (aff_cols_ints(maxc) + 1) / 2));
-  int launches = 1;
+  int rc = FEA_OK;
+  unsigned n_general = 1;  // without the affine pass every node is "general"
   if (smem_aff <= 100 * 1024 && n_elem > 0 && !affine_pass_disabled()) {
-    // stream-ordered scratch from the device's default pool (80 B per element + 1 B per node); the pool keeps what
-    // it has handed out once (release threshold), so that an assembly does not pay an OS allocation per call
-    int dev = 0;
-    cudaMemPool_t pool = nullptr;
-    FEA_TRY(check(cudaGetDevice(&dev)));
-    FEA_TRY(check(cudaDeviceGetDefaultMemPool(&pool, dev)));
-    uint64_t keep = 1ull << 31;
-    FEA_TRY(check(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)));
     const size_t geom_bytes = sizeof(double) * kGeomDoubles * (size_t)n_elem;
-    FEA_TRY(check(cudaMallocAsync(&geom, geom_bytes + (size_t)n_nodes, stream)));
+    const size_t todo_bytes = ((size_t)n_nodes + 15) & ~(size_t)15;
+    FEA_TRY(check(cudaMallocAsync(&geom, geom_bytes + todo_bytes + 16, stream)));
     todo = reinterpret_cast<uint8_t*>(geom) + geom_bytes;
-    hex8_affine_geometry_kernel<<<(unsigned)ceil_div(n_elem, 256), 256, 0, stream>>>(nodes, elements, n_elem, geom,
-                                                                                    status);
-    if (smem_aff > 48 * 1024) {
-      FEA_TRY(check(cudaFuncSetAttribute(assemble_hex8_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_aff)));
+    unsigned* counter = reinterpret_cast<unsigned*>(todo + todo_bytes);
+    rc = check(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+    if (rc == FEA_OK) {
+      hex8_affine_geometry_kernel<<<(unsigned)ceil_div(n_elem, 256), 256, 0, stream>>>(nodes, elements, n_elem, geom,
+                                                                                      counter, status);
+      if (smem_aff > 48 * 1024)
+        rc = check(cudaFuncSetAttribute(assemble_hex8_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_aff));
     }
-    const int64_t n_groups = ceil_div(n_nodes, kAffNodes);
-    const unsigned blocks_aff = (unsigned)std::min<int64_t>(ceil_div(n_groups, kAffWarps), 148LL * 64);
-    assemble_hex8_affine_kernel<<<blocks_aff, kAffWarps * 32, smem_aff, stream>>>(
-        geom, elements, n_nodes, hex8_material(E, nu), n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed, mode,
-        values, dinv, todo);
-    launches = 3;
+    if (rc == FEA_OK) {
+      const int64_t n_groups = ceil_div(n_nodes, kAffNodes);
+      const unsigned blocks_aff = (unsigned)std::min<int64_t>(ceil_div(n_groups, kAffWarps), 148LL * 64);
+      assemble_hex8_affine_kernel<<<blocks_aff, kAffWarps * 32, smem_aff, stream>>>(
+          geom, elements, n_nodes, hex8_material(E, nu), n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed, mode,
+          values, dinv, todo);
+      rc = check_launch(2);
+    }
+    if (rc == FEA_OK) rc = check(cudaMemcpyAsync(&n_general, counter, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    if (rc == FEA_OK) rc = check(cudaStreamSynchronize(stream));
   }
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, kAsmWarps * 8), 148LL * 64);
-  assemble_hex8_kernel<<<blocks, kAsmWarps * 32, smem, stream>>>(nodes, elements, n_nodes, hex8_material(E, nu), n2e_ptr,
-                                                                 n2e, node_rowptr, node_colidx, maxc, fixed, mode, values,
-                                                                 dinv, todo, status);
-  const int rc = check_launch(launches);
-  if (geom != nullptr) FEA_TRY(check(cudaFreeAsync(geom, stream)));
+  double* gauss = nullptr;
+  if (rc == FEA_OK && n_general != 0 && n_elem > 0) {
+    rc = check(cudaMallocAsync(&gauss, sizeof(double) * kGaussDoubles * 8 * (size_t)n_elem, stream));
+    if (rc == FEA_OK) {
+      hex8_gauss_geometry_kernel<<<(unsigned)ceil_div(8 * n_elem, 256), 256, 0, stream>>>(nodes, elements, n_elem, gauss,
+                                                                                         status);
+      const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, kAsmWarps * 8), 148LL * 64);
+      assemble_hex8_kernel<<<blocks, kAsmWarps * 32, smem, stream>>>(nodes, elements, n_nodes, hex8_material(E, nu),
+                                                                     n2e_ptr, n2e, node_rowptr, node_colidx, maxc, fixed,
+                                                                     mode, values, dinv, todo, gauss, status);
+      rc = check_launch(2);
+    }
+  } else if (rc == FEA_OK && n_elem == 0) {
+    // no elements at all: every node is isolated; the Gauss-point kernel writes dinv = 0 (and no values)
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n_nodes, kAsmWarps * 8), 148LL * 64);
+    assemble_hex8_kernel<<<blocks, kAsmWarps * 32, smem, stream>>>(nodes, elements, n_nodes, hex8_material(E, nu), n2e_ptr,
+                                                                   n2e, node_rowptr, node_colidx, maxc, fixed, mode,
+                                                                   values, dinv, nullptr, nullptr, status);
+    rc = check_launch();
+  }
+  if (gauss != nullptr) cudaFreeAsync(gauss, stream);
+  if (geom != nullptr) cudaFreeAsync(geom, stream);
   return rc;
 }
 

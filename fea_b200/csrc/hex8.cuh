@@ -70,11 +70,13 @@ __device__ inline void hex8_fill_shape_table(double* tab) {
 constexpr int kGradStride = 33;
 constexpr int kGradDoubles = 24 * kGradStride;
 
-// Geometry of one (element, Gauss point): J = dN X, detJ, dN_dx = J^-1 dN for the 8 nodes.
-// Returns detJ; writes the gradients to the staging area for slot t.
-__device__ __forceinline__ double hex8_geometry(const double* __restrict__ nodes, const int32_t* __restrict__ conn,
-                                                const double* __restrict__ tab, int gp, int t,
-                                                double* __restrict__ grad) {
+// Geometry of one (element, Gauss point) in two halves, so that the first can run once per element
+// (hex8_gauss_geometry_kernel, assemble.cu) and the second once per incident node:
+//   hex8_inverse_jacobian   J = dN X (utils.py:210), detJ (:211), J^-1 (:218)          -> returns detJ
+//   hex8_gradients          dN_dx = J^-1 dN for the 8 nodes (:221) -> staging area, slot t
+__device__ __forceinline__ double hex8_inverse_jacobian(const double* __restrict__ nodes,
+                                                        const int32_t* __restrict__ conn,
+                                                        const double* __restrict__ tab, int gp, double I[3][3]) {
   double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   const double* d0 = tab + (gp * 3 + 0) * 8;
   const double* d1 = tab + (gp * 3 + 1) * 8;
@@ -93,7 +95,6 @@ __device__ __forceinline__ double hex8_geometry(const double* __restrict__ nodes
   const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
   const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
   const double inv_det = 1.0 / det;
-  double I[3][3];
   I[0][0] = c00 * inv_det;
   I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * inv_det;
   I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * inv_det;
@@ -103,6 +104,14 @@ __device__ __forceinline__ double hex8_geometry(const double* __restrict__ nodes
   I[2][0] = c02 * inv_det;
   I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * inv_det;
   I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * inv_det;
+  return det;
+}
+
+__device__ __forceinline__ void hex8_gradients(const double I[3][3], const double* __restrict__ tab, int gp, int t,
+                                               double* __restrict__ grad) {
+  const double* d0 = tab + (gp * 3 + 0) * 8;
+  const double* d1 = tab + (gp * 3 + 1) * 8;
+  const double* d2 = tab + (gp * 3 + 2) * 8;
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     const double a0 = d0[a], a1 = d1[a], a2 = d2[a];
@@ -110,6 +119,15 @@ __device__ __forceinline__ double hex8_geometry(const double* __restrict__ nodes
     for (int r = 0; r < 3; ++r)
       grad[(r * 8 + gp) * kGradStride + t * 8 + a] = I[r][0] * a0 + I[r][1] * a1 + I[r][2] * a2;
   }
+}
+
+// Both halves: returns detJ; writes the gradients to the staging area for slot t.
+__device__ __forceinline__ double hex8_geometry(const double* __restrict__ nodes, const int32_t* __restrict__ conn,
+                                                const double* __restrict__ tab, int gp, int t,
+                                                double* __restrict__ grad) {
+  double I[3][3];
+  const double det = hex8_inverse_jacobian(nodes, conn, tab, gp, I);
+  hex8_gradients(I, tab, gp, t, grad);
   return det;
 }
 
