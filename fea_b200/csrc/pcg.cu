@@ -952,7 +952,7 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
   const int chunk = 32;
   const int algo = pcg_algorithm(n, false);
   // L2-sized problems on the single-reduction recurrence: one persistent kernel per chunk of iterations
-  const bool fused = algo == 1 && plan.ok && n_nodes < (int64_t)INT32_MAX / 4 && fused_supported();
+  bool fused = algo == 1 && plan.ok && n_nodes < (int64_t)INT32_MAX / 4 && fused_supported();
   FusedArgs fargs{};
   if (fused) {
     fargs.n_nodes = (int)n_nodes;
@@ -1030,6 +1030,14 @@ extern "C" int fea_pcg_solve(int64_t n_nodes, int32_t d, const int32_t* node_row
     if (fused) {
       fargs.iters = todo;
       rc = dispatch_fused(d, plan, fargs, stream);
+      if (rc != FEA_OK && enqueued == 0) {
+        // the cooperative launch was refused (e.g. the device is partitioned and cannot hold the whole grid):
+        // nothing has run yet, take the two-kernel path for this solve
+        cudaGetLastError();
+        rc = FEA_OK;
+        fused = false;
+        continue;
+      }
       if (rc == FEA_OK) profile().launches += 1;
     } else if (graph_exec != nullptr && todo == chunk) {
       rc = enqueue_iteration(sample_ev != nullptr && n_samples < kMaxSamples);
