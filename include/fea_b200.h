@@ -125,6 +125,12 @@ int fea_csr_expand(int64_t n_nodes, int32_t dof_per_node, const int32_t* node_ro
  *      fixed   [n_nodes*d] uint8 in, may be NULL: 1 = constrained (cubebeam.py:92, homogeneous)
  *      mode    FEA_ASSEMBLE_FULL: K as assembled (needed for reactions, cubebeam.py:106)
  *              FEA_ASSEMBLE_ELIMINATED: constrained rows/columns replaced by identity
+ *
+ *      fea_assemble_hex8 evaluates the geometry of an element ONCE, in stream-ordered scratch of the
+ *      device's default memory pool (80 B per element; 640 B more per element if the mesh has elements
+ *      that are not exactly affine, i.e. need the 2x2x2 quadrature of utils.py:200-237 point by point;
+ *      exactly affine elements take its closed form).  It synchronises `stream` once (a counter tells
+ *      the host whether the Gauss-point pass is needed).
  * ---------------------------------------------------------------------------------------- */
 enum { FEA_ASSEMBLE_FULL = 0, FEA_ASSEMBLE_ELIMINATED = 1 };
 
