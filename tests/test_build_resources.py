@@ -51,3 +51,19 @@ def test_vector_kernels_fit_their_launch_bounds():
     assert cgcg and cgcg[0][0] <= 80 and cgcg[0][1] == 0  # __launch_bounds__(256, 3)
     halo = [v for k, v in resources("p2p.o").items() if "p2p_halo_kernel" in k]
     assert halo and halo[0][0] <= 48  # must fit beside the persistent SpMV (6400 registers free per SM)
+
+
+def test_persistent_pcg_keeps_two_ctas_per_sm_without_spills():
+    """pcg_fused_kernel<3,3> (config 3's shape: 3 consumer groups + producer = 512 threads, 2 CTAs per SM) must stay at
+    64 registers with NO local memory: inlining the gather loop into it spilled inside the loop and cost 70 % (36
+    against 21 us per iteration) -- the loop lives in a __noinline__ function for that reason."""
+    res = resources("pcg.o")
+    hot = [v for k, v in res.items() if "pcg_fused_kernelILi3ELi3E" in k]
+    assert hot and hot[0][0] <= 64 and hot[0][1] == 0, hot
+
+
+def test_assembly_kernels_keep_five_ctas_per_sm():
+    res = resources("assemble.o")
+    for key in ("assemble_hex8_affine_kernel", "20assemble_hex8_kernel"):
+        hit = [v for k, v in res.items() if key in k]
+        assert hit and hit[0][0] <= 102 and hit[0][1] == 0, (key, hit)  # 5 x 128 threads x 102 registers <= 65536
